@@ -1,0 +1,114 @@
+/*
+ * r2l_isp.h -- C ABI of the B200-native differentiable ISP (raw Bayer -> RGB, forward + backward).
+ *
+ * This is the drop-in boundary for the hot path of aiaudit-org/raw2logit's processing/pipeline_torch.py.
+ * The reference has no FFI (it is pure Python over stock torch ops); each entry point below names the reference
+ * interface it replaces (file:line relative to the reference tree).  The host side that binds these symbols is
+ * raw2logit_b200/_lib.py (ctypes); the torch custom ops and the autograd.Function sit above it
+ * (raw2logit_b200/ops.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the current CUDA device unless noted;
+ *   - all buffers are owned by the caller (outputs, workspace); the library keeps no state between calls;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, they never synchronise;
+ *   - re-entrant from several host threads (autograd's backward thread calls r2l_isp_backward);
+ *   - return value: R2L_OK (0) or a negative R2L_ERR_* code; nothing throws across the boundary.
+ *
+ * Layouts (all row-major, contiguous):
+ *   raw      (B, H, W)     float32, or uint16 with value = u / raw_denominator (dataset.py:87: img/(2**bits-1))
+ *   out      (B, 3, H, W)  float32                                  (pipeline_torch.py:175-225 return value)
+ *   grad_out (B, 3, H, W)  float32, grad_raw (B, H, W) float32
+ *   RGGB phase of a site: par(y,x) = 2*(y&1) + (x&1) -> R, G1, G2, B  (pipeline_torch.py:256-259)
+ */
+#ifndef R2L_ISP_H
+#define R2L_ISP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R2L_ABI_VERSION 1
+
+enum {
+    R2L_OK = 0,
+    R2L_ERR_BAD_SHAPE = -1,     /* B < 0, or H < 3 or W < 3 (reference: reflect pad 2 raises, pipeline_torch.py:165,202) */
+    R2L_ERR_BAD_DTYPE = -2,     /* raw_dtype not in {R2L_F32, R2L_U16} */
+    R2L_ERR_NULL_POINTER = -3,  /* a required pointer is NULL */
+    R2L_ERR_MISALIGNED = -4,    /* out/grad pointers not 4-byte aligned, raw not element aligned */
+    R2L_ERR_WORKSPACE = -5,     /* workspace too small (see r2l_isp_backward_workspace_bytes) */
+    R2L_ERR_CUDA = -6,          /* a CUDA runtime call failed; r2l_isp_last_cuda_error() has the code */
+    R2L_ERR_BAD_ARGUMENT = -7   /* inconsistent flags / unsupported mode */
+};
+
+enum { R2L_F32 = 0, R2L_U16 = 1 };
+
+/* The 132 trainable scalars + the two fixed colour-space matrices of ParametrizedProcessing
+ * (pipeline_torch.py:154-171).  Device pointers to float32, each tensor contiguous in its torch layout. */
+typedef struct r2l_isp_params {
+    const float* black_level;        /* (4,)        :154 */
+    const float* white_balance;      /* (1,3)       :155 */
+    const float* colour_correction;  /* (3,3) [k][c] :156 */
+    const float* gamma_correct;      /* (1,)        :158 */
+    const float* debayer_weight;     /* (3,3,3,3) [k][c][i][j]  Debayer :228-237 */
+    const float* sharpen_weight;     /* (1,1,3,3)   :162-163 */
+    const float* gauss_weight;       /* (1,1,5,5)   :165-166 */
+    const float* rgb2yuv;            /* (3,3) buffer M_RGB_2_YUV :170 */
+    const float* yuv2rgb;            /* (3,3) buffer M_YUV_2_RGB :171 */
+} r2l_isp_params;
+
+/* Offsets of each parameter group inside the flat 132-float gradient vector written by r2l_isp_backward. */
+enum {
+    R2L_G_BLACK_LEVEL = 0,    /* 4  */
+    R2L_G_WHITE_BALANCE = 4,  /* 3  */
+    R2L_G_COLOUR = 7,         /* 9  */
+    R2L_G_GAMMA = 16,         /* 1  */
+    R2L_G_DEBAYER = 17,       /* 81 */
+    R2L_G_SHARPEN = 98,       /* 9  */
+    R2L_G_GAUSS = 107,        /* 25 */
+    R2L_NUM_PARAM_GRADS = 132
+};
+
+/* Optional fused tail of the forward (both may be NULL):
+ *   additive  (3,H,W) float32 broadcast over B       -- additive_layer, pipeline_torch.py:129-131, 212-214
+ *   affine    6 floats {scale[3], shift[3]}: out = o*scale[c] + shift[c]
+ *             -- BatchNorm2d(3, affine=False) in eval mode folded to scale/shift, pipeline_torch.py:168, 216-217 */
+typedef struct r2l_isp_tail {
+    const float* additive;
+    const float* affine;
+} r2l_isp_tail;
+
+int r2l_isp_abi_version(void);
+const char* r2l_isp_error_string(int code);
+int r2l_isp_last_cuda_error(void);
+
+/* Fused forward: replaces ParametrizedProcessing.forward (pipeline_torch.py:175-225) minus stage tracking:
+ * raw2rgb :183 -> Debayer :187 -> WB :190 -> CCM :191 -> RGB2YUV :194 -> sharpen(Y) :195 -> Gaussian(Y) :202
+ * -> YUV2RGB :203 -> clip :206 -> gamma :209 [-> additive :213] [-> eval-BN :217].  tail may be NULL. */
+int r2l_isp_forward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
+                    const r2l_isp_params* params, const r2l_isp_tail* tail, float* out, void* stream);
+
+/* Fused backward: replaces the autograd graph of the same chain (79 nodes).
+ * grad_out is dL/d(o) of the gamma stage (i.e. already pulled back through additive / BN by the caller).
+ * grad_raw may be NULL (the training case: raw does not require grad).  grad_params receives
+ * R2L_NUM_PARAM_GRADS floats laid out per the R2L_G_* offsets.  workspace: r2l_isp_backward_workspace_bytes(). */
+size_t r2l_isp_backward_workspace_bytes(int B, int H, int W);
+int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
+                     const r2l_isp_params* params, const float* grad_out,
+                     float* grad_raw, float* grad_params, void* workspace, size_t workspace_bytes, void* stream);
+
+/* CFA split, replaces raw2rgb (pipeline_torch.py:240-283) / RawToRGB.forward (:65-80).
+ * reduce_size=1: out (B,C,H/2,W/2) packed (C=3 averages the greens), needs even H,W (the reference raises
+ * otherwise); reduce_size=0: out (B,C,H,W) zero-filled mosaic.  black_level: NULL or 4 floats (device). */
+int r2l_isp_mosaic(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
+                   const float* black_level, int reduce_size, int out_channels, float* out, void* stream);
+/* Its adjoint with respect to raw: grad_raw (B,H,W) from grad_out in the layout above. */
+int r2l_isp_mosaic_backward(const float* grad_out, int B, int H, int W, int reduce_size, int out_channels,
+                            float* grad_raw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R2L_ISP_H */

@@ -1,0 +1,10 @@
+// Tile configurations shared by the CUDA kernels (isp_kernels.cu) and the host emulation (tests/emu).
+#pragma once
+#include "isp_core.cuh"
+
+namespace r2l {
+using FwdDefault = FwdCfg<32, 64, 256>;
+using BwdNoRaw = BwdCfg<32, 64, 256, false>;
+using BwdWithRaw = BwdCfg<32, 64, 256, true>;
+constexpr int kMaxCtas = 2048;          // upper bound on persistent CTAs == rows of the statistics workspace
+}  // namespace r2l

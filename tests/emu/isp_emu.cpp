@@ -1,0 +1,78 @@
+// Host emulation of the CUDA CTA functions (raw2logit_b200/csrc/isp_core.cuh) -- TEST INFRASTRUCTURE ONLY.
+// g++ compiles the same source the GPU kernels are made of, with threads of a CTA run one after another and
+// barriers turned into loop boundaries.  tests/test_emu_logic.py compares it with the oracle so that indexing,
+// border handling and the hand-derived adjoints are checked in a container that has no GPU.
+// Never loaded by the raw2logit_b200 package; it is not a fallback.
+#define R2L_HOST_EMU 1
+#include <vector>
+#include <cstring>
+#include "../../include/r2l_isp.h"
+#include "../../raw2logit_b200/csrc/isp_config.h"
+
+using namespace r2l;
+
+static Params to_params(const r2l_isp_params* p) {
+    Params q;
+    q.black_level = p->black_level; q.white_balance = p->white_balance; q.colour_correction = p->colour_correction;
+    q.gamma_correct = p->gamma_correct; q.debayer_weight = p->debayer_weight; q.sharpen_weight = p->sharpen_weight;
+    q.gauss_weight = p->gauss_weight; q.rgb2yuv = p->rgb2yuv; q.yuv2rgb = p->yuv2rgb;
+    return q;
+}
+
+template <class Cfg, typename RawT>
+static void run_forward(const FwdArgs& a, int n_cta) {
+    const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
+    std::vector<float> smem(Cfg::kSmemFloats);
+    for (int cta = 0; cta < n_cta; ++cta) fwd_cta<Cfg, RawT>(cta, n_cta, a, grid, smem.data());
+}
+
+template <class Cfg, typename RawT>
+static void run_backward(const BwdArgs& a, int n_cta, float* grads) {
+    const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
+    std::vector<float> smem(Cfg::kSmemFloats);
+    for (int cta = 0; cta < n_cta; ++cta) bwd_cta<Cfg, RawT>(cta, n_cta, a, grid, smem.data());
+    // finish (same arithmetic as isp_backward_finish_kernel)
+    std::vector<float> tmem((sizeof(Tables) + 3) / 4);
+    Tables* T = reinterpret_cast<Tables*>(tmem.data());
+    R2L_BUILD_TABLES(64, a.P, T)
+    double S[kNumStats];
+    for (int s = 0; s < kNumStats; ++s) {
+        double sum = 0.0;
+        for (int c = 0; c < n_cta; ++c) sum += (double)a.partials[(size_t)c * kStatPitch + s];
+        S[s] = sum;
+    }
+    for (int e = 0; e < R2L_NUM_PARAM_GRADS; ++e) grads[e] = finish_grad(e, S, T);
+}
+
+extern "C" {
+
+// all pointers are HOST pointers here
+int emu_isp_forward(const void* raw, int raw_dtype, float denom, int B, int H, int W, const r2l_isp_params* params,
+                    const r2l_isp_tail* tail, float* out, int n_cta) {
+    if (H < 3 || W < 3) return R2L_ERR_BAD_SHAPE;
+    FwdArgs a;
+    a.raw = raw; a.denom = denom; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
+    a.additive = tail ? tail->additive : nullptr; a.affine = tail ? tail->affine : nullptr; a.out = out;
+    if (raw_dtype == R2L_F32) run_forward<FwdDefault, float>(a, n_cta);
+    else run_forward<FwdDefault, uint16_t>(a, n_cta);
+    return R2L_OK;
+}
+
+int emu_isp_backward(const void* raw, int raw_dtype, float denom, int B, int H, int W, const r2l_isp_params* params,
+                     const float* grad_out, float* grad_raw, float* grad_params, int n_cta) {
+    if (H < 3 || W < 3) return R2L_ERR_BAD_SHAPE;
+    std::vector<float> partials((size_t)n_cta * kStatPitch, 0.f);
+    BwdArgs a;
+    a.raw = raw; a.denom = denom; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
+    a.gout = grad_out; a.graw = grad_raw; a.partials = partials.data();
+    if (grad_raw) {
+        if (raw_dtype == R2L_F32) run_backward<BwdWithRaw, float>(a, n_cta, grad_params);
+        else run_backward<BwdWithRaw, uint16_t>(a, n_cta, grad_params);
+    } else {
+        if (raw_dtype == R2L_F32) run_backward<BwdNoRaw, float>(a, n_cta, grad_params);
+        else run_backward<BwdNoRaw, uint16_t>(a, n_cta, grad_params);
+    }
+    return R2L_OK;
+}
+
+}
