@@ -91,13 +91,18 @@ int r2l_isp_forward(const void* raw, int raw_dtype, float raw_denominator, int B
                     const r2l_isp_params* params, const r2l_isp_tail* tail, float* out, void* stream);
 
 /* Fused backward: replaces the autograd graph of the same chain (79 nodes).
- * grad_out is dL/d(o) of the gamma stage (i.e. already pulled back through additive / BN by the caller).
+ * grad_out is dL/d(output); grad_out_scale (NULL or 3 floats) is the per-channel factor of the affine tail the
+ * forward applied (eval-mode BN), so that dL/d(o) = grad_out * scale[c] is formed inside the kernel.
  * grad_raw may be NULL (the training case: raw does not require grad).  grad_params receives
  * R2L_NUM_PARAM_GRADS floats laid out per the R2L_G_* offsets.  workspace: r2l_isp_backward_workspace_bytes(). */
 size_t r2l_isp_backward_workspace_bytes(int B, int H, int W);
 int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
-                     const r2l_isp_params* params, const float* grad_out,
+                     const r2l_isp_params* params, const float* grad_out, const float* grad_out_scale,
                      float* grad_raw, float* grad_params, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[c][i] = scale[c] * sum_b x[b][c][i]  (scale may be NULL): gradient of the broadcast additive_layer
+ * (pipeline_torch.py:212-214), x = grad_out (B,C,HW), out (C,HW).  Deterministic (fixed summation order). */
+int r2l_isp_batch_sum(const float* x, const float* scale, int B, int C, int HW, float* out, void* stream);
 
 /* CFA split, replaces raw2rgb (pipeline_torch.py:240-283) / RawToRGB.forward (:65-80).
  * reduce_size=1: out (B,C,H/2,W/2) packed (C=3 averages the greens), needs even H,W (the reference raises

@@ -383,6 +383,7 @@ struct BwdArgs {
     const void* raw; float denom; int B, H, W;
     Params P;
     const float* gout;     // (B,3,H,W)
+    const float* gscale;   // null or 3 per-channel factors applied to gout (affine tail of the forward)
     float* graw;           // (B,H,W) or null
     float* partials;       // [n_cta][kStatPitch]
 };
@@ -452,7 +453,8 @@ R2L_HD void bwd_tile(int tid, int phase, const BwdArgs& a, const Tables* T, int 
                 const bool owned = gy >= ty0 && gy < ty0 + TH && gx >= tx0 && gx < tx0 + TW;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float G = a.gout[((size_t)b * 3 + k) * plane + pix];
+                    float G = a.gout[((size_t)b * 3 + k) * plane + pix];
+                    if (a.gscale) G *= a.gscale[k];
                     const float go = G * t.o[k];
                     if (owned) acc.sg = fmaf_(go, t.l2[k], acc.sg);
                     const bool pass = (t.r[k] >= kClipLo) && (t.r[k] <= kClipHi);   // clamp backward mask, inclusive

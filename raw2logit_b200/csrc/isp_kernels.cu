@@ -77,6 +77,16 @@ __global__ void mosaic_kernel(const RawT* raw, float denom, int B, int H, int W,
     }
 }
 
+__global__ void batch_sum_kernel(const float* x, const float* scale, int B, int C, int HW, float* out) {
+    const size_t n = (size_t)C * HW;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += x[(size_t)b * n + i];
+        if (scale) s *= scale[i / HW];
+        out[i] = s;
+    }
+}
+
 __global__ void mosaic_backward_kernel(const float* gout, int B, int H, int W, int reduce_size, int C, float* graw) {
     const size_t plane = (size_t)H * W, n = (size_t)B * plane;
     const int h2 = H / 2, w2 = W / 2;
@@ -217,8 +227,8 @@ size_t r2l_isp_backward_workspace_bytes(int B, int H, int W) {
 }
 
 int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
-                     const r2l_isp_params* params, const float* grad_out, float* grad_raw, float* grad_params,
-                     void* workspace, size_t workspace_bytes, void* stream) {
+                     const r2l_isp_params* params, const float* grad_out, const float* grad_out_scale,
+                     float* grad_raw, float* grad_params, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_common(raw, raw_dtype, B, H, W, params);
     if (rc != R2L_OK) return rc;
     if (!grad_params || !workspace || (B > 0 && !grad_out)) return R2L_ERR_NULL_POINTER;
@@ -232,7 +242,7 @@ int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int 
     }
     BwdArgs a;
     a.raw = raw; a.denom = raw_denominator; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
-    a.gout = grad_out; a.graw = grad_raw; a.partials = static_cast<float*>(workspace);
+    a.gout = grad_out; a.gscale = grad_out_scale; a.graw = grad_raw; a.partials = static_cast<float*>(workspace);
     if (grad_raw) {
         return raw_dtype == R2L_F32 ? launch_backward<BwdWithRaw, float>(a, grad_params, st)
                                     : launch_backward<BwdWithRaw, uint16_t>(a, grad_params, st);
@@ -276,6 +286,18 @@ int r2l_isp_mosaic_backward(const float* grad_out, int B, int H, int W, int redu
     const int blocks = (int)((n + threads - 1) / threads < 148 * 16 ? (n + threads - 1) / threads : 148 * 16);
     mosaic_backward_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, B, H, W, reduce_size,
                                                                                       out_channels, grad_raw);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? R2L_OK : cuda_fail(e);
+}
+
+int r2l_isp_batch_sum(const float* x, const float* scale, int B, int C, int HW, float* out, void* stream) {
+    if (B < 0 || C < 0 || HW < 0) return R2L_ERR_BAD_SHAPE;
+    const size_t n = (size_t)C * HW;
+    if (n == 0) return R2L_OK;
+    if (!out || (B > 0 && !x)) return R2L_ERR_NULL_POINTER;
+    const int threads = 256;
+    const int blocks = (int)((n + threads - 1) / threads < 148 * 16 ? (n + threads - 1) / threads : 148 * 16);
+    batch_sum_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(x, scale, B, C, HW, out);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);
 }

@@ -59,12 +59,12 @@ int emu_isp_forward(const void* raw, int raw_dtype, float denom, int B, int H, i
 }
 
 int emu_isp_backward(const void* raw, int raw_dtype, float denom, int B, int H, int W, const r2l_isp_params* params,
-                     const float* grad_out, float* grad_raw, float* grad_params, int n_cta) {
+                     const float* grad_out, const float* grad_scale, float* grad_raw, float* grad_params, int n_cta) {
     if (H < 3 || W < 3) return R2L_ERR_BAD_SHAPE;
     std::vector<float> partials((size_t)n_cta * kStatPitch, 0.f);
     BwdArgs a;
     a.raw = raw; a.denom = denom; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
-    a.gout = grad_out; a.graw = grad_raw; a.partials = partials.data();
+    a.gout = grad_out; a.gscale = grad_scale; a.graw = grad_raw; a.partials = partials.data();
     if (grad_raw) {
         if (raw_dtype == R2L_F32) run_backward<BwdWithRaw, float>(a, n_cta, grad_params);
         else run_backward<BwdWithRaw, uint16_t>(a, n_cta, grad_params);
