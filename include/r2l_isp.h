@@ -38,7 +38,7 @@ enum {
     R2L_ERR_BAD_DTYPE = -2,     /* raw_dtype not in {R2L_F32, R2L_U16} */
     R2L_ERR_NULL_POINTER = -3,  /* a required pointer is NULL */
     R2L_ERR_MISALIGNED = -4,    /* out/grad pointers not 4-byte aligned, raw not element aligned */
-    R2L_ERR_WORKSPACE = -5,     /* workspace too small (see r2l_isp_backward_workspace_bytes) */
+    R2L_ERR_WORKSPACE = -5,     /* workspace too small (see r2l_isp_workspace_bytes) */
     R2L_ERR_CUDA = -6,          /* a CUDA runtime call failed; r2l_isp_last_cuda_error() has the code */
     R2L_ERR_BAD_ARGUMENT = -7   /* inconsistent flags / unsupported mode */
 };
@@ -90,15 +90,34 @@ int r2l_isp_last_cuda_error(void);
 int r2l_isp_forward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
                     const r2l_isp_params* params, const r2l_isp_tail* tail, float* out, void* stream);
 
+/* Workspace every call below accepts (a fixed upper bound, independent of the shape). */
+size_t r2l_isp_workspace_bytes(int B, int H, int W);
+
+/* Fused forward + train-mode BatchNorm2d(3, affine=False) tail (pipeline_torch.py:168, 216-217; train.py:196
+ * always enables it): forward kernel that also reduces per-channel sum / sum of squares, a finish kernel that
+ * forms batch mean / biased variance, writes saved_affine = {1/sqrt(var+eps)[3], -mean/sqrt(var+eps)[3]} and
+ * updates running_mean / running_var in place like torch (momentum, unbiased variance; either may be NULL), and
+ * an in-place normalisation of out.  additive may be NULL. */
+int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
+                             const r2l_isp_params* params, const float* additive, float* out,
+                             float* running_mean, float* running_var, float momentum, float eps,
+                             float* saved_affine, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of that tail, part 1: reduces sum(grad_out), sum(grad_out * out) per channel and writes the 15-float
+ * grad_tail {gs[3], c1[3], c2[3], ysc[3], ysh[3]} that r2l_isp_backward consumes. */
+int r2l_isp_bn_backward_prepare(const float* grad_out, const float* out, const float* saved_affine, int B, int H,
+                                int W, float* grad_tail, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fused backward: replaces the autograd graph of the same chain (79 nodes).
- * grad_out is dL/d(output); grad_out_scale (NULL or 3 floats) is the per-channel factor of the affine tail the
- * forward applied (eval-mode BN), so that dL/d(o) = grad_out * scale[c] is formed inside the kernel.
- * grad_raw may be NULL (the training case: raw does not require grad).  grad_params receives
- * R2L_NUM_PARAM_GRADS floats laid out per the R2L_G_* offsets.  workspace: r2l_isp_backward_workspace_bytes(). */
-size_t r2l_isp_backward_workspace_bytes(int B, int H, int W);
+ * grad_out is dL/d(output).  grad_tail (NULL or 15 floats {gs, c1, c2, ysc, ysh} x 3 channels) describes the
+ * BatchNorm tail the forward applied: dL/d(o) = gs*(grad_out - c1 - c2*yhat), yhat = (o + additive)*ysc + ysh,
+ * formed inside the kernel (eval mode: gs = 1/sqrt(running_var+eps), c1 = c2 = 0).  additive (NULL or (3,H,W))
+ * is only read for yhat.  grad_raw may be NULL (the training case: raw does not require grad).  grad_params
+ * receives R2L_NUM_PARAM_GRADS floats laid out per the R2L_G_* offsets. */
 int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
-                     const r2l_isp_params* params, const float* grad_out, const float* grad_out_scale,
-                     float* grad_raw, float* grad_params, void* workspace, size_t workspace_bytes, void* stream);
+                     const r2l_isp_params* params, const float* grad_out, const float* grad_tail,
+                     const float* additive, float* grad_raw, float* grad_params, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* out[c][i] = scale[c] * sum_b x[b][c][i]  (scale may be NULL): gradient of the broadcast additive_layer
  * (pipeline_torch.py:212-214), x = grad_out (B,C,HW), out (C,HW).  Deterministic (fixed summation order). */

@@ -13,6 +13,8 @@
 #ifdef R2L_HOST_EMU
 #include <cmath>
 #include <algorithm>
+#include <vector>
+#include <cstring>
 #define R2L_HD inline
 #define R2L_FOR_THREADS(NT) for (int tid = 0; tid < (NT); ++tid)
 #define R2L_SYNC()
@@ -60,6 +62,19 @@ R2L_HD float fmaf_(float a, float b, float c) {
     return __fmaf_rn(a, b, c);
 #endif
 }
+#ifndef R2L_HOST_EMU
+__device__ __forceinline__ float warp_sum_all(float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// sums lanes of equal (lane & 1): lanes 0 and 1 end up holding the even / odd totals
+__device__ __forceinline__ float warp_sum_same_parity(float v) {
+#pragma unroll
+    for (int o = 16; o >= 2; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
 R2L_HD int imin(int a, int b) { return a < b ? a : b; }
 R2L_HD int imax(int a, int b) { return a > b ? a : b; }
 
@@ -282,7 +297,9 @@ struct FwdArgs {
     const float* additive;     // (3,H,W) or null
     const float* affine;       // {scale[3], shift[3]} or null
     float* out;
+    float* chan_partials;      // STATS only: [n_cta][kChanPitch] per-CTA sums of o and o*o per channel
 };
+constexpr int kChanPitch = 8;
 
 struct TileGrid {
     int tiles_x, tiles_y, n;
@@ -299,12 +316,22 @@ inline TileGrid make_grid(int B, int H, int W, int TH, int TW) {
     return g;
 }
 
-template <class Cfg, typename RawT>
+struct ChanAcc { float s[6]; };     // sum o[k], sum o[k]^2
+
+template <class Cfg, typename RawT, bool STATS>
 R2L_HD void fwd_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid, float* smem) {
     constexpr int TH = Cfg::TH, TW = Cfg::TW, NT = Cfg::NT;
     Tables* T = reinterpret_cast<Tables*>(smem);
     typename Cfg::RegR R; typename Cfg::RegY0 Y0; typename Cfg::RegY1 Y1;
     R.s = smem + Cfg::kTableFloats; Y0.s = R.s + Cfg::RegR::n; Y1.s = Y0.s + Cfg::RegY0::n;
+#ifdef R2L_HOST_EMU
+    std::vector<ChanAcc> cacc(NT);
+    for (int i = 0; i < NT; ++i) for (int k = 0; k < 6; ++k) cacc[i].s[k] = 0.f;
+#else
+    ChanAcc cacc;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cacc.s[k] = 0.f;
+#endif
     R2L_BUILD_TABLES(NT, a.P, T)
     const int H = a.H, W = a.W;
     const size_t plane = (size_t)H * W;
@@ -334,12 +361,42 @@ R2L_HD void fwd_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid, 
                 for (int k = 0; k < 3; ++k) {
                     float o = t.o[k];
                     if (a.additive) o += a.additive[(size_t)k * plane + pix];
+                    if (STATS) {
+                        ChanAcc& c = R2L_ACC(cacc, tid);
+                        c.s[k] += o;
+                        c.s[3 + k] = fmaf_(o, o, c.s[3 + k]);
+                    }
                     if (a.affine) o = fmaf_(o, a.affine[k], a.affine[3 + k]);
                     a.out[((size_t)b * 3 + k) * plane + pix] = o;
                 }
             }
         } }
         R2L_SYNC();   // smem is rewritten by the next tile
+    }
+    if (STATS) {
+        float* part = a.chan_partials + (size_t)cta * kChanPitch;
+#ifdef R2L_HOST_EMU
+        for (int k = 0; k < 6; ++k) {
+            double sum = 0.0;
+            for (int i = 0; i < NT; ++i) sum += cacc[i].s[k];
+            part[k] = (float)sum;
+        }
+#else
+        constexpr int NW = NT / 32;
+        float* red = smem + Cfg::kTableFloats;             // regions are dead
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const float v = warp_sum_all(cacc.s[k]);
+            if (lane == 0) red[warp * 6 + k] = v;
+        }
+        __syncthreads();
+        if (tid < 6) {
+            float sum = 0.f;
+            for (int w = 0; w < NW; ++w) sum += red[w * 6 + tid];
+            part[tid] = sum;
+        }
+#endif
     }
 }
 
@@ -383,7 +440,9 @@ struct BwdArgs {
     const void* raw; float denom; int B, H, W;
     Params P;
     const float* gout;     // (B,3,H,W)
-    const float* gscale;   // null or 3 per-channel factors applied to gout (affine tail of the forward)
+    const float* gtail;    // null or 15 floats {gs[3], c1[3], c2[3], ysc[3], ysh[3]}: the BatchNorm tail's backward,
+                           // dL/do = gs*(G - c1 - c2*yhat) with yhat = (o + additive)*ysc + ysh (eval mode: c1=c2=0)
+    const float* additive; // (3,H,W) or null, only read when gtail is given
     float* graw;           // (B,H,W) or null
     float* partials;       // [n_cta][kStatPitch]
 };
@@ -454,7 +513,12 @@ R2L_HD void bwd_tile(int tid, int phase, const BwdArgs& a, const Tables* T, int 
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     float G = a.gout[((size_t)b * 3 + k) * plane + pix];
-                    if (a.gscale) G *= a.gscale[k];
+                    if (a.gtail) {
+                        float yhat = t.o[k];
+                        if (a.additive) yhat += a.additive[(size_t)k * plane + pix];
+                        yhat = fmaf_(yhat, a.gtail[9 + k], a.gtail[12 + k]);
+                        G = a.gtail[k] * (G - a.gtail[3 + k] - a.gtail[6 + k] * yhat);
+                    }
                     const float go = G * t.o[k];
                     if (owned) acc.sg = fmaf_(go, t.l2[k], acc.sg);
                     const bool pass = (t.r[k] >= kClipLo) && (t.r[k] <= kClipHi);   // clamp backward mask, inclusive
@@ -667,19 +731,6 @@ R2L_HD int mosaic_channel(int par, int C) { return C == 3 ? ch_of(par) : par; }
 
 namespace r2l {
 
-#ifndef R2L_HOST_EMU
-__device__ __forceinline__ float warp_sum_all(float v) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-// sums lanes of equal (lane & 1): lanes 0 and 1 end up holding the even / odd totals
-__device__ __forceinline__ float warp_sum_same_parity(float v) {
-#pragma unroll
-    for (int o = 16; o >= 2; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-#endif
 
 template <class Cfg, typename RawT>
 R2L_HD void bwd_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid, float* smem) {

@@ -14,10 +14,95 @@ namespace r2l {
 // ---------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------
-template <class Cfg, typename RawT>
+template <class Cfg, typename RawT, bool STATS>
 __global__ void __launch_bounds__(Cfg::NT) isp_forward_kernel(FwdArgs a, TileGrid grid) {
     extern __shared__ __align__(16) float smem[];
-    fwd_cta<Cfg, RawT>(blockIdx.x, gridDim.x, a, grid, smem);
+    fwd_cta<Cfg, RawT, STATS>(blockIdx.x, gridDim.x, a, grid, smem);
+}
+
+// ---- train-mode BatchNorm2d(3, affine=False) tail (pipeline_torch.py:168, 216-217) -------------------------
+// per-CTA channel sums -> batch mean / biased variance -> {scale, shift}; running statistics updated in place
+// exactly like torch (momentum update, unbiased variance for the running estimate).
+__global__ void bn_finish_kernel(const float* partials, int n_cta, double count, float momentum, float eps,
+                                 float* running_mean, float* running_var, float* affine) {
+    const int c = threadIdx.x;
+    if (c >= 3) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < n_cta; ++i) {
+        s1 += (double)partials[(size_t)i * kChanPitch + c];
+        s2 += (double)partials[(size_t)i * kChanPitch + 3 + c];
+    }
+    const double mean = s1 / count;
+    double var = s2 / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double inv = 1.0 / sqrt(var + (double)eps);
+    affine[c] = (float)inv;
+    affine[3 + c] = (float)(-mean * inv);
+    if (running_mean) running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+    if (running_var) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+    }
+}
+
+// x[b][c][i] = x*scale[c] + shift[c], in place
+__global__ void affine_inplace_kernel(float* x, const float* affine, int BC, int HW) {
+    const int bc = blockIdx.y;
+    if (bc >= BC) return;
+    const int c = bc % 3;
+    const float sc = affine[c], sh = affine[3 + c];
+    float* p = x + (size_t)bc * HW;
+    if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        float4* p4 = reinterpret_cast<float4*>(p);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) {
+            float4 v = p4[i];
+            v.x = fmaf(v.x, sc, sh); v.y = fmaf(v.y, sc, sh); v.z = fmaf(v.z, sc, sh); v.w = fmaf(v.w, sc, sh);
+            p4[i] = v;
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+            p[i] = fmaf(p[i], sc, sh);
+    }
+}
+
+// backward of the batch statistics: per channel sum(gy), sum(gy*y) with y the normalised output
+constexpr int kBnBwdBlocks = 128;
+__global__ void __launch_bounds__(256) bn_backward_stats_kernel(const float* gy, const float* y, int B, int HW,
+                                                                float* partials /* [3][kBnBwdBlocks][2] */) {
+    const int c = blockIdx.y;
+    float s1 = 0.f, s2 = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const size_t base = ((size_t)b * 3 + c) * HW;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+            const float g = gy[base + i];
+            s1 += g;
+            s2 = fmaf(g, y[base + i], s2);
+        }
+    }
+    __shared__ float red[2][8];
+    s1 = warp_sum_all(s1); s2 = warp_sum_all(s2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+        partials[((size_t)c * kBnBwdBlocks + blockIdx.x) * 2 + threadIdx.x] = t;
+    }
+}
+__global__ void bn_backward_finish_kernel(const float* partials, const float* affine, double count, float* gtail) {
+    const int c = threadIdx.x;
+    if (c >= 3) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < kBnBwdBlocks; ++i) {
+        s1 += (double)partials[((size_t)c * kBnBwdBlocks + i) * 2];
+        s2 += (double)partials[((size_t)c * kBnBwdBlocks + i) * 2 + 1];
+    }
+    gtail[c] = affine[c];                       // gs  = 1/sqrt(var+eps)
+    gtail[3 + c] = (float)(s1 / count);         // c1  = mean(gy)
+    gtail[6 + c] = (float)(s2 / count);         // c2  = mean(gy * yhat)
+    gtail[9 + c] = affine[c];                   // ysc
+    gtail[12 + c] = affine[3 + c];              // ysh
 }
 
 template <class Cfg, typename RawT>
@@ -155,13 +240,14 @@ static int persistent_grid(K kernel, int threads, size_t smem, int n_tiles, int*
     return R2L_OK;
 }
 
-template <class Cfg, typename RawT>
-static int launch_forward(const FwdArgs& a, cudaStream_t st) {
+template <class Cfg, typename RawT, bool STATS>
+static int launch_forward(const FwdArgs& a, cudaStream_t st, int* grid_used = nullptr) {
     const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
     int g = 0;
-    int rc = persistent_grid(isp_forward_kernel<Cfg, RawT>, Cfg::NT, Cfg::kSmemBytes, grid.n, &g);
+    int rc = persistent_grid(isp_forward_kernel<Cfg, RawT, STATS>, Cfg::NT, Cfg::kSmemBytes, grid.n, &g);
     if (rc != R2L_OK) return rc;
-    isp_forward_kernel<Cfg, RawT><<<g, Cfg::NT, Cfg::kSmemBytes, st>>>(a, grid);
+    isp_forward_kernel<Cfg, RawT, STATS><<<g, Cfg::NT, Cfg::kSmemBytes, st>>>(a, grid);
+    if (grid_used) *grid_used = g;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);
 }
@@ -215,26 +301,71 @@ int r2l_isp_forward(const void* raw, int raw_dtype, float raw_denominator, int B
     a.raw = raw; a.denom = raw_denominator; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.additive = tail ? tail->additive : nullptr;
     a.affine = tail ? tail->affine : nullptr;
-    a.out = out;
+    a.out = out; a.chan_partials = nullptr;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return raw_dtype == R2L_F32 ? launch_forward<FwdDefault, float>(a, st)
-                                : launch_forward<FwdDefault, uint16_t>(a, st);
+    return raw_dtype == R2L_F32 ? launch_forward<FwdDefault, float, false>(a, st)
+                                : launch_forward<FwdDefault, uint16_t, false>(a, st);
 }
 
-size_t r2l_isp_backward_workspace_bytes(int B, int H, int W) {
+size_t r2l_isp_workspace_bytes(int B, int H, int W) {
     (void)B; (void)H; (void)W;
     return (size_t)kMaxCtas * kStatPitch * sizeof(float);
 }
 
+int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
+                             const r2l_isp_params* params, const float* additive, float* out,
+                             float* running_mean, float* running_var, float momentum, float eps,
+                             float* saved_affine, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(raw, raw_dtype, B, H, W, params);
+    if (rc != R2L_OK) return rc;
+    if (!out || !saved_affine || !workspace) return R2L_ERR_NULL_POINTER;
+    if (!aligned(out, 4) || !aligned(workspace, 8)) return R2L_ERR_MISALIGNED;
+    if (workspace_bytes < r2l_isp_workspace_bytes(B, H, W)) return R2L_ERR_WORKSPACE;
+    if ((size_t)B * H * W < 2) return R2L_ERR_BAD_SHAPE;     // torch: "Expected more than 1 value per channel"
+    FwdArgs a;
+    a.raw = raw; a.denom = raw_denominator; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
+    a.additive = additive; a.affine = nullptr; a.out = out; a.chan_partials = static_cast<float*>(workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int g = 0;
+    rc = raw_dtype == R2L_F32 ? launch_forward<FwdDefault, float, true>(a, st, &g)
+                              : launch_forward<FwdDefault, uint16_t, true>(a, st, &g);
+    if (rc != R2L_OK) return rc;
+    bn_finish_kernel<<<1, 32, 0, st>>>(a.chan_partials, g, (double)B * H * W, momentum, eps, running_mean,
+                                       running_var, saved_affine);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    const int hw = H * W;
+    dim3 grid((unsigned)((hw / 4 + 255) / 256 < 64 ? (hw / 4 + 255) / 256 + 1 : 64), (unsigned)(B * 3));
+    affine_inplace_kernel<<<grid, 256, 0, st>>>(out, saved_affine, B * 3, hw);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? R2L_OK : cuda_fail(e);
+}
+
+int r2l_isp_bn_backward_prepare(const float* grad_out, const float* out, const float* saved_affine, int B, int H,
+                                int W, float* grad_tail, void* workspace, size_t workspace_bytes, void* stream) {
+    if (B < 1 || H < 1 || W < 1) return R2L_ERR_BAD_SHAPE;
+    if (!grad_out || !out || !saved_affine || !grad_tail || !workspace) return R2L_ERR_NULL_POINTER;
+    if (workspace_bytes < (size_t)3 * kBnBwdBlocks * 2 * sizeof(float)) return R2L_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* partials = static_cast<float*>(workspace);
+    bn_backward_stats_kernel<<<dim3(kBnBwdBlocks, 3), 256, 0, st>>>(grad_out, out, B, H * W, partials);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    bn_backward_finish_kernel<<<1, 32, 0, st>>>(partials, saved_affine, (double)B * H * W, grad_tail);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? R2L_OK : cuda_fail(e);
+}
+
 int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
-                     const r2l_isp_params* params, const float* grad_out, const float* grad_out_scale,
-                     float* grad_raw, float* grad_params, void* workspace, size_t workspace_bytes, void* stream) {
+                     const r2l_isp_params* params, const float* grad_out, const float* grad_tail,
+                     const float* additive, float* grad_raw, float* grad_params, void* workspace,
+                     size_t workspace_bytes, void* stream) {
     int rc = check_common(raw, raw_dtype, B, H, W, params);
     if (rc != R2L_OK) return rc;
     if (!grad_params || !workspace || (B > 0 && !grad_out)) return R2L_ERR_NULL_POINTER;
     if (!aligned(grad_out, 4) || !aligned(grad_raw, 4) || !aligned(grad_params, 4) || !aligned(workspace, 8))
         return R2L_ERR_MISALIGNED;
-    if (workspace_bytes < r2l_isp_backward_workspace_bytes(B, H, W)) return R2L_ERR_WORKSPACE;
+    if (workspace_bytes < r2l_isp_workspace_bytes(B, H, W)) return R2L_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (B == 0) {
         cudaError_t e = cudaMemsetAsync(grad_params, 0, R2L_NUM_PARAM_GRADS * sizeof(float), st);
@@ -242,7 +373,7 @@ int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int 
     }
     BwdArgs a;
     a.raw = raw; a.denom = raw_denominator; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
-    a.gout = grad_out; a.gscale = grad_out_scale; a.graw = grad_raw; a.partials = static_cast<float*>(workspace);
+    a.gout = grad_out; a.gtail = grad_tail; a.additive = additive; a.graw = grad_raw; a.partials = static_cast<float*>(workspace);
     if (grad_raw) {
         return raw_dtype == R2L_F32 ? launch_backward<BwdWithRaw, float>(a, grad_params, st)
                                     : launch_backward<BwdWithRaw, uint16_t>(a, grad_params, st);

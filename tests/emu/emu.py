@@ -71,7 +71,7 @@ def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0):
     return out
 
 
-def backward(raw, state, grad_out, need_raw_grad=True, n_cta=3, denom=65535.0, grad_scale=None):
+def backward(raw, state, grad_out, need_raw_grad=True, n_cta=3, denom=65535.0, grad_tail=None, additive=None):
     raw = np.ascontiguousarray(raw)
     dtype = 1 if raw.dtype == np.uint16 else 0
     if dtype == 0:
@@ -81,10 +81,12 @@ def backward(raw, state, grad_out, need_raw_grad=True, n_cta=3, denom=65535.0, g
     g = _f32(grad_out)
     graw = np.full((b, h, w), np.nan, dtype=np.float32) if need_raw_grad else None
     gpar = np.full(132, np.nan, dtype=np.float32)
-    gs = None if grad_scale is None else _f32(grad_scale)
+    gs = None if grad_tail is None else _f32(grad_tail)
+    add = None if additive is None else _f32(additive)
     rc = lib().emu_isp_backward(ctypes.c_void_p(raw.ctypes.data), dtype, ctypes.c_float(denom), b, h, w,
                                 ctypes.byref(p), ctypes.c_void_p(g.ctypes.data),
                                 None if gs is None else ctypes.c_void_p(gs.ctypes.data),
+                                None if add is None else ctypes.c_void_p(add.ctypes.data),
                                 None if graw is None else ctypes.c_void_p(graw.ctypes.data),
                                 ctypes.c_void_p(gpar.ctypes.data), n_cta)
     assert rc == 0, rc

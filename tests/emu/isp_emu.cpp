@@ -23,7 +23,7 @@ template <class Cfg, typename RawT>
 static void run_forward(const FwdArgs& a, int n_cta) {
     const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
     std::vector<float> smem(Cfg::kSmemFloats);
-    for (int cta = 0; cta < n_cta; ++cta) fwd_cta<Cfg, RawT>(cta, n_cta, a, grid, smem.data());
+    for (int cta = 0; cta < n_cta; ++cta) fwd_cta<Cfg, RawT, false>(cta, n_cta, a, grid, smem.data());
 }
 
 template <class Cfg, typename RawT>
@@ -53,18 +53,20 @@ int emu_isp_forward(const void* raw, int raw_dtype, float denom, int B, int H, i
     FwdArgs a;
     a.raw = raw; a.denom = denom; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.additive = tail ? tail->additive : nullptr; a.affine = tail ? tail->affine : nullptr; a.out = out;
+    a.chan_partials = nullptr;
     if (raw_dtype == R2L_F32) run_forward<FwdDefault, float>(a, n_cta);
     else run_forward<FwdDefault, uint16_t>(a, n_cta);
     return R2L_OK;
 }
 
 int emu_isp_backward(const void* raw, int raw_dtype, float denom, int B, int H, int W, const r2l_isp_params* params,
-                     const float* grad_out, const float* grad_scale, float* grad_raw, float* grad_params, int n_cta) {
+                     const float* grad_out, const float* grad_tail, const float* additive, float* grad_raw,
+                     float* grad_params, int n_cta) {
     if (H < 3 || W < 3) return R2L_ERR_BAD_SHAPE;
     std::vector<float> partials((size_t)n_cta * kStatPitch, 0.f);
     BwdArgs a;
     a.raw = raw; a.denom = denom; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
-    a.gout = grad_out; a.gscale = grad_scale; a.graw = grad_raw; a.partials = partials.data();
+    a.gout = grad_out; a.gtail = grad_tail; a.additive = additive; a.graw = grad_raw; a.partials = partials.data();
     if (grad_raw) {
         if (raw_dtype == R2L_F32) run_backward<BwdWithRaw, float>(a, n_cta, grad_params);
         else run_backward<BwdWithRaw, uint16_t>(a, n_cta, grad_params);
