@@ -175,7 +175,7 @@ def run_ours(args):
     outs = [torch.empty(B, 3, H, W, device=dev) for _ in range(S)]
     graws = [torch.empty(B, H, W, device=dev) for _ in range(S)]
     gpar = torch.empty(_lib.NUM_PARAM_GRADS, device=dev)
-    nws = lib.r2l_isp_backward_workspace_bytes(B, H, W)
+    nws = lib.r2l_isp_workspace_bytes(B, H, W)
     wsb = torch.empty(nws // 4, device=dev)
     ptensors = [mod.black_level, mod.white_balance, mod.colour_correction, mod.gamma_correct, mod.debayer.weight,
                 mod.sharpening_filter.weight, mod.gaussian_blur.weight, mod.M_RGB_2_YUV, mod.M_YUV_2_RGB]
@@ -192,7 +192,7 @@ def run_ours(args):
 
     def step_backward(s):
         return lib.r2l_isp_backward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, H, W, ctypes.byref(params),
-                                    vp(gouts[s].data_ptr()), None, vp(graws[s].data_ptr()), vp(gpar.data_ptr()),
+                                    vp(gouts[s].data_ptr()), None, None, vp(graws[s].data_ptr()), vp(gpar.data_ptr()),
                                     vp(wsb.data_ptr()), nws, sp)
 
     def barrier():

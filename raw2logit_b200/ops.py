@@ -19,8 +19,11 @@ _PARAMS_SCHEMA = ("Tensor black_level, Tensor white_balance, Tensor colour_corre
 
 _library = torch.library.Library(_NS, "DEF")
 _library.define(f"forward(Tensor raw, {_PARAMS_SCHEMA}, Tensor? additive, Tensor? affine, float raw_denominator) -> Tensor")
-_library.define(f"backward(Tensor raw, {_PARAMS_SCHEMA}, Tensor grad_out, Tensor? grad_scale, bool need_raw_grad, "
-                "float raw_denominator) -> (Tensor, Tensor)")
+_library.define(f"forward_bn_train(Tensor raw, {_PARAMS_SCHEMA}, Tensor? additive, Tensor(a!)? running_mean, "
+                "Tensor(b!)? running_var, float momentum, float eps, float raw_denominator) -> (Tensor, Tensor)")
+_library.define("bn_backward_prepare(Tensor grad_out, Tensor out, Tensor saved_affine) -> Tensor")
+_library.define(f"backward(Tensor raw, {_PARAMS_SCHEMA}, Tensor grad_out, Tensor? grad_tail, Tensor? additive, "
+                "bool need_raw_grad, float raw_denominator) -> (Tensor, Tensor)")
 _library.define("mosaic(Tensor raw, Tensor? black_level, bool reduce_size, int out_channels, float raw_denominator) -> Tensor")
 _library.define("mosaic_backward(Tensor grad_out, int H, int W, bool reduce_size, int out_channels) -> Tensor")
 _library.define("batch_sum(Tensor x, Tensor? scale) -> Tensor")
@@ -86,20 +89,62 @@ def _forward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, affine,
     return out
 
 
-def _backward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, grad_scale, need_raw_grad, raw_denominator):
+def _forward_bn_train_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, running_mean, running_var,
+                           momentum, eps, raw_denominator):
+    lib = _lib.load()
+    b, h, w = _check_shape(raw)
+    if b * h * w < 2:
+        raise ValueError("Expected more than 1 value per channel when training")
+    raw, code = _raw_input(raw)
+    with torch.cuda.device(raw.device):
+        params, keep = _pack_params((bl, wb, ccm, gamma, wd, ws, wg, m1, m2))
+        add = None if additive is None else _f32c(additive, 3 * h * w, "additive")
+        for t, name in ((running_mean, "running_mean"), (running_var, "running_var")):
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != 3):
+                raise TypeError(f"{name} must be a contiguous float32 tensor with 3 elements")
+        out = torch.empty((b, 3, h, w), dtype=torch.float32, device=raw.device)
+        saved = torch.empty(6, dtype=torch.float32, device=raw.device)
+        nbytes = lib.r2l_isp_workspace_bytes(b, h, w)
+        ws_buf = torch.empty(nbytes // 4, dtype=torch.float32, device=raw.device)
+        rc = lib.r2l_isp_forward_bn_train(_ptr(raw), code, raw_denominator, b, h, w, ctypes.byref(params), _ptr(add),
+                                          _ptr(out), _ptr(running_mean), _ptr(running_var), momentum, eps,
+                                          _ptr(saved), _ptr(ws_buf), nbytes, _stream())
+    _lib.check(rc, "r2l_isp_forward_bn_train")
+    return out, saved
+
+
+def _bn_backward_prepare_cuda(grad_out, out, saved_affine):
+    lib = _lib.load()
+    b, _, h, w = out.shape
+    with torch.cuda.device(out.device):
+        g = _f32c(grad_out, out.numel(), "grad_out")
+        y = _f32c(out, out.numel(), "out")
+        sa = _f32c(saved_affine, 6, "saved_affine")
+        tail = torch.empty(15, dtype=torch.float32, device=out.device)
+        nbytes = lib.r2l_isp_workspace_bytes(b, h, w)
+        ws_buf = torch.empty(nbytes // 4, dtype=torch.float32, device=out.device)
+        rc = lib.r2l_isp_bn_backward_prepare(_ptr(g), _ptr(y), _ptr(sa), b, h, w, _ptr(tail), _ptr(ws_buf), nbytes,
+                                             _stream())
+    _lib.check(rc, "r2l_isp_bn_backward_prepare")
+    return tail
+
+
+def _backward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, grad_tail, additive, need_raw_grad,
+                   raw_denominator):
     lib = _lib.load()
     b, h, w = _check_shape(raw)
     raw, code = _raw_input(raw)
     with torch.cuda.device(raw.device):
         params, keep = _pack_params((bl, wb, ccm, gamma, wd, ws, wg, m1, m2))
         g = _f32c(grad_out, b * 3 * h * w, "grad_out")
-        gs = None if grad_scale is None else _f32c(grad_scale, 3, "grad_scale")
+        gs = None if grad_tail is None else _f32c(grad_tail, 15, "grad_tail")
+        add = None if additive is None else _f32c(additive, 3 * h * w, "additive")
         graw = torch.empty((b, h, w), dtype=torch.float32, device=raw.device) if need_raw_grad else None
         gpar = torch.empty(_lib.NUM_PARAM_GRADS, dtype=torch.float32, device=raw.device)
-        nbytes = lib.r2l_isp_backward_workspace_bytes(b, h, w)
+        nbytes = lib.r2l_isp_workspace_bytes(b, h, w)
         ws_buf = torch.empty(nbytes // 4, dtype=torch.float32, device=raw.device)
         rc = lib.r2l_isp_backward(_ptr(raw), code, raw_denominator, b, h, w, ctypes.byref(params), _ptr(g), _ptr(gs),
-                                  _ptr(graw), _ptr(gpar), _ptr(ws_buf), nbytes, _stream())
+                                  _ptr(add), _ptr(graw), _ptr(gpar), _ptr(ws_buf), nbytes, _stream())
     _lib.check(rc, "r2l_isp_backward")
     if graw is None:
         graw = torch.empty(0, dtype=torch.float32, device=raw.device)
@@ -152,6 +197,8 @@ def _batch_sum_cuda(x, scale):
 
 
 _library.impl("forward", _forward_cuda, "CUDA")
+_library.impl("forward_bn_train", _forward_bn_train_cuda, "CUDA")
+_library.impl("bn_backward_prepare", _bn_backward_prepare_cuda, "CUDA")
 _library.impl("backward", _backward_cuda, "CUDA")
 _library.impl("mosaic", _mosaic_cuda, "CUDA")
 _library.impl("mosaic_backward", _mosaic_backward_cuda, "CUDA")
@@ -161,41 +208,69 @@ _ops = getattr(torch.ops, _NS)
 
 
 class FusedISP(torch.autograd.Function):
-    """raw (B,H,W) + 7 parameter tensors + 2 buffers [+ additive, affine] -> (B,3,H,W).
+    """raw (B,H,W) + 7 parameter tensors + 2 buffers [+ additive] [+ BatchNorm tail] -> (B,3,H,W).
 
-    Saves only ``raw`` and the (tiny) parameters; the backward kernel recomputes the forward per tile.
-    Gradients are returned for raw (if needed), the 7 parameter tensors and the additive layer; the colour-space
-    buffers and the affine tail (BatchNorm running statistics) get none, as in the reference.
+    Saves only ``raw`` and the (tiny) parameters (plus the output when the train-mode BatchNorm tail is on, whose
+    backward needs it); the backward kernel recomputes the forward per tile.  Gradients are returned for raw (if
+    needed), the 7 parameter tensors and the additive layer; the colour-space buffers and the BatchNorm statistics
+    get none, as in the reference.
+
+    bn_mode: 0 = no tail, 1 = eval (affine from running statistics), 2 = train (batch statistics, running
+    statistics updated in place by the kernel).
     """
 
     @staticmethod
-    def forward(ctx, raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, affine, raw_denominator):
-        out = _ops.forward(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, affine, raw_denominator)
-        ctx.save_for_backward(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, affine)
+    def forward(ctx, raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, bn_mode, running_mean, running_var,
+                momentum, eps, raw_denominator):
+        params = (bl, wb, ccm, gamma, wd, ws, wg, m1, m2)
+        saved_affine, out_saved = None, None
+        if bn_mode == 2:
+            out, saved_affine = _ops.forward_bn_train(raw, *params, additive, running_mean, running_var,
+                                                      momentum, eps, raw_denominator)
+            ctx.mark_non_differentiable(saved_affine)
+            out_saved = out
+        elif bn_mode == 1:
+            scale = torch.rsqrt(running_var + eps)
+            saved_affine = torch.cat([scale, -running_mean * scale])
+            out = _ops.forward(raw, *params, additive, saved_affine, raw_denominator)
+        else:
+            out = _ops.forward(raw, *params, additive, None, raw_denominator)
+        ctx.save_for_backward(raw, *params, additive, saved_affine, out_saved)
+        ctx.bn_mode = bn_mode
         ctx.raw_denominator = raw_denominator
-        ctx.has_additive = additive is not None
-        ctx.additive_shape = None if additive is None else additive.shape
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, affine = ctx.saved_tensors
+        raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, saved_affine, out_saved = ctx.saved_tensors
+        params = (bl, wb, ccm, gamma, wd, ws, wg, m1, m2)
         need_raw = ctx.needs_input_grad[0]
-        scale = None if affine is None else affine[:3]
         grad_out = grad_out.contiguous()
-        grads = [None] * 13
+        grads = [None] * 17
+        tail = None
+        if ctx.bn_mode == 2:
+            tail = _ops.bn_backward_prepare(grad_out, out_saved, saved_affine)
+        elif ctx.bn_mode == 1:
+            tail = torch.cat([saved_affine[:3], saved_affine.new_zeros(12)])
         if need_raw or any(ctx.needs_input_grad[1:8]):
-            graw, gpar = _ops.backward(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, scale, need_raw,
-                                       ctx.raw_denominator)
+            graw, gpar = _ops.backward(raw, *params, grad_out, tail, additive if ctx.bn_mode == 2 else None,
+                                       need_raw, ctx.raw_denominator)
             if need_raw:
                 grads[0] = graw if raw.dtype == torch.float32 else graw.to(raw.dtype)
             for slot, name in enumerate(_lib.PARAM_FIELDS[:7], start=1):
                 if ctx.needs_input_grad[slot]:
                     off, n, shape = _lib.GRAD_LAYOUT[name]
                     grads[slot] = gpar[off:off + n].view(shape)
-        if ctx.has_additive and ctx.needs_input_grad[10]:
-            grads[10] = _ops.batch_sum(grad_out, scale).view(ctx.additive_shape)
+        if additive is not None and ctx.needs_input_grad[10]:
+            if ctx.bn_mode == 2:
+                # d/d(additive) = sum_b gs*(G - c1 - c2*yhat); yhat is the saved output
+                gs, c1, c2 = (tail[0:3].view(1, 3, 1, 1), tail[3:6].view(1, 3, 1, 1), tail[6:9].view(1, 3, 1, 1))
+                geff = gs * (grad_out - c1 - c2 * out_saved)
+                grads[10] = _ops.batch_sum(geff, None).view(additive.shape)
+            else:
+                scale = None if saved_affine is None else saved_affine[:3]
+                grads[10] = _ops.batch_sum(grad_out, scale).view(additive.shape)
         return tuple(grads)
 
 
@@ -217,6 +292,8 @@ class Mosaic(torch.autograd.Function):
 
 
 def fused_isp(raw, black_level, white_balance, colour_correction, gamma_correct, debayer_weight, sharpen_weight,
-              gauss_weight, rgb2yuv, yuv2rgb, additive=None, affine=None, raw_denominator=65535.0):
+              gauss_weight, rgb2yuv, yuv2rgb, additive=None, bn_mode=0, running_mean=None, running_var=None,
+              momentum=0.1, eps=1e-5, raw_denominator=65535.0):
     return FusedISP.apply(raw, black_level, white_balance, colour_correction, gamma_correct, debayer_weight,
-                          sharpen_weight, gauss_weight, rgb2yuv, yuv2rgb, additive, affine, float(raw_denominator))
+                          sharpen_weight, gauss_weight, rgb2yuv, yuv2rgb, additive, int(bn_mode), running_mean,
+                          running_var, float(momentum), float(eps), float(raw_denominator))

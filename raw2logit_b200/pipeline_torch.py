@@ -170,11 +170,6 @@ class ParametrizedProcessing(nn.Module):
         self.additive_layer = None  # this can be added in later
         self.raw_bits = 16          # uint16 ingest: value = u / (2**raw_bits - 1)   (dataset.py:87)
 
-    def _eval_bn_affine(self):
-        bn = self.batch_norm
-        scale = torch.rsqrt(bn.running_var + bn.eps)
-        return torch.cat([scale, -bn.running_mean * scale])
-
     def forward(self, raw):
         assert raw.ndim == 3, f"needs dims (B, H, W), got {raw.shape}"
         _require_cuda(raw)
@@ -184,19 +179,26 @@ class ParametrizedProcessing(nn.Module):
             raise NotImplementedError("track_stages=True (staged kernels) lands in the next milestone")
 
         bn = self.batch_norm
-        use_batch_stats = bn is not None and (bn.training or bn.running_mean is None)
-        affine = None
-        if bn is not None and not use_batch_stats:
-            affine = self._eval_bn_affine()
+        bn_mode, rm, rv, momentum, eps = 0, None, None, 0.1, 1e-5
+        if bn is not None:
+            eps = bn.eps
+            use_batch_stats = bn.training or bn.running_mean is None
+            bn_mode = 2 if use_batch_stats else 1
+            rm, rv = bn.running_mean, bn.running_var
+            if use_batch_stats and bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)                      # nn.BatchNorm2d bookkeeping
+                momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            elif use_batch_stats:
+                rm, rv = None, None                                  # batch statistics, nothing to update
         additive = self.additive_layer
         if additive is not None and additive.numel() != 3 * raw.shape[1] * raw.shape[2]:
-            raise RuntimeError(f"additive_layer {tuple(additive.shape)} does not match a {raw.shape[1]}x{raw.shape[2]} frame")
+            raise RuntimeError(f"additive_layer {tuple(additive.shape)} does not match a "
+                               f"{raw.shape[1]}x{raw.shape[2]} frame")
         rgb = ops.fused_isp(raw, self.black_level, self.white_balance, self.colour_correction, self.gamma_correct,
                             self.debayer.weight, self.sharpening_filter.weight, self.gaussian_blur.weight,
-                            self.M_RGB_2_YUV, self.M_YUV_2_RGB, additive=additive, affine=affine,
+                            self.M_RGB_2_YUV, self.M_YUV_2_RGB, additive=additive, bn_mode=bn_mode,
+                            running_mean=rm, running_var=rv, momentum=momentum, eps=eps,
                             raw_denominator=float(2 ** self.raw_bits - 1))
-        if use_batch_stats:
-            rgb = bn(rgb)       # TODO(next milestone): fused two-pass train-mode BatchNorm kernels
         self.buffer['processed_rgb'] = rgb
         return rgb
 

@@ -91,3 +91,27 @@ def test_eval_batchnorm_tail_is_an_affine_epilogue():
     shift = (-rm.astype(np.float64) * scale).astype(np.float32)
     out = emu.forward(c.raw.numpy(), c.state, affine=np.concatenate([scale, shift]))
     assert maxabs(out, c.f32["out"]) <= 5e-5       # output is scaled by 1/sqrt(var) ~ 6: tolerance scales with it
+
+
+@pytest.mark.parametrize("name", ["bn_train", "bn_train_additive"])
+@pytest.mark.parametrize("cot", ["mean", "ramp"])
+def test_train_batchnorm_tail_backward(name, cot):
+    """dL/do = gs*(G - mean(G) - yhat*mean(G*yhat)) formed inside the backward kernel (15-float grad_tail)."""
+    c = GoldenCase(name)
+    add = None if c.additive is None else c.additive
+    o, _ = isp_oracle.forward(c.raw.double(), isp_oracle.cast_state(c.state, torch.float64),
+                              additive=None if add is None else add.double(), dtype=torch.float64)
+    mean = o.mean(dim=(0, 2, 3))
+    var = o.var(dim=(0, 2, 3), unbiased=False)
+    inv = 1.0 / torch.sqrt(var + 1e-5)
+    y = (o - mean.view(1, 3, 1, 1)) * inv.view(1, 3, 1, 1)
+    assert maxabs(y, c.f64["out"]) <= 1e-9
+    g = isp_oracle.cotangent(tuple(y.shape), cot, torch.float64)
+    c1 = g.mean(dim=(0, 2, 3))
+    c2 = (g * y).mean(dim=(0, 2, 3))
+    tail = torch.cat([inv, c1, c2, inv, -mean * inv]).float().numpy()
+    grads = emu.backward(c.raw.numpy(), c.state, g.float().numpy(), grad_tail=tail,
+                         additive=None if add is None else add.numpy()[0])
+    for k, v in grads.items():
+        ref = c.f64[f"grad.{cot}.{k}"]
+        assert maxabs(v.reshape(ref.shape), ref) <= 2e-5 * max(1.0, float(np.abs(ref).max())), (name, k)

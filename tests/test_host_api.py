@@ -26,7 +26,7 @@ def test_library_exports_every_symbol_the_header_declares(lib):
         assert hasattr(lib, name), name
     assert lib.r2l_isp_abi_version() == 1
     assert b"shape" in lib.r2l_isp_error_string(-1)
-    assert lib.r2l_isp_backward_workspace_bytes(64, 256, 256) >= 155 * 4
+    assert lib.r2l_isp_workspace_bytes(64, 256, 256) >= 155 * 4
 
 
 def test_argument_validation_happens_before_any_cuda_call(lib):
