@@ -15,9 +15,9 @@ namespace r2l {
 // kernels
 // ---------------------------------------------------------------------------------------------------------
 template <class Cfg, typename RawT, bool STATS>
-__global__ void __launch_bounds__(Cfg::NT) isp_forward_kernel(FwdArgs a, TileGrid grid) {
+__global__ void __launch_bounds__(Cfg::NT, 2) isp_forward_kernel(FwdArgs a, TileGrid grid) {
     extern __shared__ __align__(16) float smem[];
-    fwd_cta<Cfg, RawT, STATS>(blockIdx.x, gridDim.x, a, grid, smem);
+    fwd2_cta<Cfg, RawT, STATS>(blockIdx.x, gridDim.x, a, grid, smem);
 }
 
 // ---- train-mode BatchNorm2d(3, affine=False) tail (pipeline_torch.py:168, 216-217) -------------------------
@@ -242,7 +242,7 @@ static int persistent_grid(K kernel, int threads, size_t smem, int n_tiles, int*
 
 template <class Cfg, typename RawT, bool STATS>
 static int launch_forward(const FwdArgs& a, cudaStream_t st, int* grid_used = nullptr) {
-    const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
+    const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);     // tiles of image pairs
     int g = 0;
     int rc = persistent_grid(isp_forward_kernel<Cfg, RawT, STATS>, Cfg::NT, Cfg::kSmemBytes, grid.n, &g);
     if (rc != R2L_OK) return rc;
@@ -303,8 +303,8 @@ int r2l_isp_forward(const void* raw, int raw_dtype, float raw_denominator, int B
     a.affine = tail ? tail->affine : nullptr;
     a.out = out; a.chan_partials = nullptr;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return raw_dtype == R2L_F32 ? launch_forward<FwdDefault, float, false>(a, st)
-                                : launch_forward<FwdDefault, uint16_t, false>(a, st);
+    return raw_dtype == R2L_F32 ? launch_forward<Fwd2Default, float, false>(a, st)
+                                : launch_forward<Fwd2Default, uint16_t, false>(a, st);
 }
 
 size_t r2l_isp_workspace_bytes(int B, int H, int W) {
@@ -327,8 +327,8 @@ int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominat
     a.additive = additive; a.affine = nullptr; a.out = out; a.chan_partials = static_cast<float*>(workspace);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int g = 0;
-    rc = raw_dtype == R2L_F32 ? launch_forward<FwdDefault, float, true>(a, st, &g)
-                              : launch_forward<FwdDefault, uint16_t, true>(a, st, &g);
+    rc = raw_dtype == R2L_F32 ? launch_forward<Fwd2Default, float, true>(a, st, &g)
+                              : launch_forward<Fwd2Default, uint16_t, true>(a, st, &g);
     if (rc != R2L_OK) return rc;
     bn_finish_kernel<<<1, 32, 0, st>>>(a.chan_partials, g, (double)B * H * W, momentum, eps, running_mean,
                                        running_var, saved_affine);

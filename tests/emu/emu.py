@@ -10,6 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(HERE, "isp_emu.cpp")
 LIB = os.path.join(HERE, "libisp_emu.so")
 DEPS = [SRC, os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_core.cuh"),
+        os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_fwd2.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_config.h"), os.path.join(ROOT, "include", "r2l_isp.h")]
 
 PARAM_FIELDS = ["black_level", "white_balance", "colour_correction", "gamma_correct", "debayer.weight",
@@ -54,7 +55,7 @@ def _params(state):
     return p, keep
 
 
-def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0):
+def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0, version=2, chan_sums=None):
     raw = np.ascontiguousarray(raw)
     dtype = 1 if raw.dtype == np.uint16 else 0
     if dtype == 0:
@@ -66,7 +67,8 @@ def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0):
     tail = Tail(None if add is None else add.ctypes.data, None if aff is None else aff.ctypes.data)
     out = np.full((b, 3, h, w), np.nan, dtype=np.float32)
     rc = lib().emu_isp_forward(ctypes.c_void_p(raw.ctypes.data), dtype, ctypes.c_float(denom), b, h, w,
-                               ctypes.byref(p), ctypes.byref(tail), ctypes.c_void_p(out.ctypes.data), n_cta)
+                               ctypes.byref(p), ctypes.byref(tail), ctypes.c_void_p(out.ctypes.data), n_cta, version,
+                               None if chan_sums is None else ctypes.c_void_p(chan_sums.ctypes.data))
     assert rc == 0, rc
     return out
 

@@ -20,10 +20,19 @@ static Params to_params(const r2l_isp_params* p) {
 }
 
 template <class Cfg, typename RawT>
-static void run_forward(const FwdArgs& a, int n_cta) {
+static void run_forward_v1(const FwdArgs& a, int n_cta) {
     const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
     std::vector<float> smem(Cfg::kSmemFloats);
     for (int cta = 0; cta < n_cta; ++cta) fwd_cta<Cfg, RawT, false>(cta, n_cta, a, grid, smem.data());
+}
+
+template <class Cfg, typename RawT, bool STATS>
+static void run_forward(const FwdArgs& a, int n_cta) {
+    const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);
+    std::vector<float> smem(Cfg::kSmemBytes / 4 + 4);
+    float* base = smem.data();
+    while (reinterpret_cast<uintptr_t>(base) % 16) ++base;          // the kernels assume 16-byte aligned shared memory
+    for (int cta = 0; cta < n_cta; ++cta) fwd2_cta<Cfg, RawT, STATS>(cta, n_cta, a, grid, base);
 }
 
 template <class Cfg, typename RawT>
@@ -48,14 +57,29 @@ extern "C" {
 
 // all pointers are HOST pointers here
 int emu_isp_forward(const void* raw, int raw_dtype, float denom, int B, int H, int W, const r2l_isp_params* params,
-                    const r2l_isp_tail* tail, float* out, int n_cta) {
+                    const r2l_isp_tail* tail, float* out, int n_cta, int version, double* chan_sums) {
     if (H < 3 || W < 3) return R2L_ERR_BAD_SHAPE;
     FwdArgs a;
     a.raw = raw; a.denom = denom; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.additive = tail ? tail->additive : nullptr; a.affine = tail ? tail->affine : nullptr; a.out = out;
     a.chan_partials = nullptr;
-    if (raw_dtype == R2L_F32) run_forward<FwdDefault, float>(a, n_cta);
-    else run_forward<FwdDefault, uint16_t>(a, n_cta);
+    if (version == 1) {
+        if (raw_dtype == R2L_F32) run_forward_v1<FwdDefault, float>(a, n_cta);
+        else run_forward_v1<FwdDefault, uint16_t>(a, n_cta);
+    } else if (chan_sums) {
+        std::vector<float> partials((size_t)n_cta * kChanPitch, 0.f);
+        a.chan_partials = partials.data();
+        if (raw_dtype == R2L_F32) run_forward<Fwd2Default, float, true>(a, n_cta);
+        else run_forward<Fwd2Default, uint16_t, true>(a, n_cta);
+        for (int k = 0; k < 6; ++k) {
+            double s = 0.0;
+            for (int c = 0; c < n_cta; ++c) s += partials[(size_t)c * kChanPitch + k];
+            chan_sums[k] = s;
+        }
+    } else {
+        if (raw_dtype == R2L_F32) run_forward<Fwd2Default, float, false>(a, n_cta);
+        else run_forward<Fwd2Default, uint16_t, false>(a, n_cta);
+    }
     return R2L_OK;
 }
 

@@ -115,3 +115,15 @@ def test_train_batchnorm_tail_backward(name, cot):
     for k, v in grads.items():
         ref = c.f64[f"grad.{cot}.{k}"]
         assert maxabs(v.reshape(ref.shape), ref) <= 2e-5 * max(1.0, float(np.abs(ref).max())), (name, k)
+
+
+def test_forward_v1_and_v2_agree_and_channel_statistics():
+    raw = syn.smooth_scene(3, 70, 130, "drone", seed=12)
+    st = syn.perturbed_state(isp_oracle.default_state(syn.CAMERA_PRESETS["drone"]))
+    v1 = emu.forward(raw.numpy(), st, version=1)
+    sums = np.zeros(6, dtype=np.float64)
+    v2 = emu.forward(raw.numpy(), st, version=2, chan_sums=sums)
+    assert maxabs(v1, v2) <= 1e-6
+    o = v2.astype(np.float64)
+    want = np.concatenate([o.sum(axis=(0, 2, 3)), (o * o).sum(axis=(0, 2, 3))])
+    assert np.allclose(sums, want, rtol=1e-5)
