@@ -39,17 +39,57 @@ R2L_HD void st2(f2* p, f2 a, f2 b) {
     f4 v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = b.y;
     *reinterpret_cast<f4*>(p) = v;
 }
-// 6 consecutive sites starting at an ODD site index: 64 + 128 + 128 + 64 bit accesses
-R2L_HD void ld6_odd(const f2* p, f2 v[6]) {
-    v[0] = p[0];
-    ld2(p + 1, v[1], v[2]);
-    ld2(p + 3, v[3], v[4]);
-    v[5] = p[5];
+// Plane rows are stored "chunk de-interleaved": a row of pitch P sites keeps its even 16-byte chunks (site pairs
+// 4q, 4q+1) in the first half and its odd chunks (4q+2, 4q+3) in the second half.  A thread owns the 4-site run
+// 4q..4q+3, so lane-consecutive runs read/write lane-consecutive 16-byte chunks in each half: every LDS.128 /
+// STS.128 of a warp is bank-conflict free (the natural layout gave 2-way conflicts: 32 B lane stride).
+template <int P> R2L_HD int phys(int s) { return ((s >> 1) & 1) * (P / 2) + ((s >> 2) << 1) + (s & 1); }
+// sites c-1 .. c+4 of a row, c = 4q;  eb = row*P + 2q
+template <int P> R2L_HD void ld6(const f2* pl, int eb, f2 v[6]) {
+    const int ob = eb + P / 2;
+    v[0] = pl[ob - 1];
+    ld2(pl + eb, v[1], v[2]);
+    ld2(pl + ob, v[3], v[4]);
+    v[5] = pl[eb + 2];
 }
-// 8 consecutive sites starting at an EVEN site index
-R2L_HD void ld8_even(const f2* p, f2 v[8]) {
-    ld2(p, v[0], v[1]); ld2(p + 2, v[2], v[3]); ld2(p + 4, v[4], v[5]); ld2(p + 6, v[6], v[7]);
+// sites c-2 .. c+5
+template <int P> R2L_HD void ld8(const f2* pl, int eb, f2 v[8]) {
+    const int ob = eb + P / 2;
+    ld2(pl + ob - 2, v[0], v[1]); ld2(pl + eb, v[2], v[3]); ld2(pl + ob, v[4], v[5]); ld2(pl + eb + 2, v[6], v[7]);
 }
+// sites c .. c+3
+template <int P> R2L_HD void st4(f2* pl, int eb, f2 a0, f2 a1, f2 a2, f2 a3) {
+    st2(pl + eb, a0, a1); st2(pl + eb + P / 2, a2, a3);
+}
+template <int P> R2L_HD void ld4(const f2* pl, int eb, f2 v[4]) {
+    ld2(pl + eb, v[0], v[1]); ld2(pl + eb + P / 2, v[2], v[3]);
+}
+
+#ifndef R2L_HOST_EMU
+// ---- TMA (cp.async.bulk.tensor) + mbarrier: the raw window of both images is fetched by the copy engine into a
+// staging buffer while the previous tile is still being computed ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "R2L_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra R2L_WAIT_%=;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one thread: arm the barrier with the byte count and launch the 3-D box copy {x, y, image}
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int x, int y, int z, uint64_t* bar, uint32_t bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic-proxy reads of dst are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+#endif
 
 // parameter tables in the layout the v2 phases read with vector loads
 struct Tables2 {
@@ -83,7 +123,11 @@ template <int TH_, int TW_, int NT_> struct Fwd2Cfg {
     static constexpr int G = TW / 4;                  // 4-site groups per tile row
     static constexpr int kTableFloats = (sizeof(Tables2) + 15) / 16 * 4;
     static constexpr int kXR = RH * P, kY0 = Y0H * P, kUV = TH * TW;          // sizes in float2 sites
-    static constexpr size_t kSmemBytes = (size_t)kTableFloats * 4 + (size_t)(kXR + kY0 + 2 * kUV) * 8;
+    static constexpr size_t kPlaneBytes = (size_t)kTableFloats * 4 + (size_t)(kXR + kY0 + 2 * kUV) * 8;
+    static constexpr size_t kStageOffset = (kPlaneBytes + 127) / 128 * 128;       // TMA destination: 128-byte aligned
+    static constexpr size_t kStageBytes = (size_t)2 * RH * P * 4;                 // [image][row][P] of the raw element
+    static constexpr size_t kSmemBytes = kPlaneBytes;                             // generic loader
+    static constexpr size_t kSmemBytesTma = kStageOffset + kStageBytes + 16;      // + staging + mbarrier
     static_assert(TW % 8 == 0 && TH % 2 == 0 && NT % G == 0 && ((NT / G) % 2) == 0, "row phase must be per-thread");
     static_assert(Y1H * P <= kXR, "Y1 aliases the raw window");
 };
@@ -96,8 +140,9 @@ R2L_HD void decode_pair_tile(const TileGrid& grid, int id, int TH, int TW, int B
     b1 = b0 + 1 < B ? b0 + 1 : b0;
 }
 
-template <class Cfg, typename RawT, bool STATS>
-R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid, float* smem) {
+// TMA = true (device only): the raw window arrives through a tensor map (box P x RH x 2, out-of-bounds zero filled)
+template <class Cfg, typename RawT, bool STATS, bool TMA = false>
+R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid, float* smem, const void* tmap = nullptr) {
     constexpr int TH = Cfg::TH, TW = Cfg::TW, NT = Cfg::NT, P = Cfg::P, G = Cfg::G;
     Tables2* T2 = reinterpret_cast<Tables2*>(smem);
     Tables* T = &T2->base;
@@ -121,6 +166,23 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
     const int H = a.H, W = a.W;
     const size_t plane = (size_t)H * W;
     const bool vec_ok = (W % 4) == 0;
+#ifndef R2L_HOST_EMU
+    RawT* stage = reinterpret_cast<RawT*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset + Cfg::kStageBytes);
+    uint32_t tma_phase = 0;
+    constexpr uint32_t kTmaBytes = 2u * Cfg::RH * P * sizeof(RawT);
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(mbar, 1);
+            if (cta < grid.n) {
+                int pb0, pb1, py0, px0;
+                decode_pair_tile(grid, cta, TH, TW, a.B, pb0, pb1, py0, px0);
+                tma_load_3d(stage, tmap, px0 - 8, py0 - 4, pb0, mbar, kTmaBytes);
+            }
+        }
+        __syncthreads();
+    }
+#endif
     for (int tile = cta; tile < grid.n; tile += n_cta) {
         int b0, b1, ty0, tx0;
         decode_pair_tile(grid, tile, TH, TW, a.B, b0, b1, ty0, tx0);
@@ -128,18 +190,72 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
         const RawT* imgB = static_cast<const RawT*>(a.raw) + (size_t)b1 * plane;
         const bool interior = ty0 >= 4 && tx0 >= 8 && ty0 + TH + 4 <= H && tx0 + TW + 8 <= W;
 
+#ifndef R2L_HOST_EMU
+        if (TMA) {
+            // ---- P1 (TMA): staged [image][row][P] -> XR site pairs; the next tile's window is requested right after ----
+            mbar_wait(mbar, tma_phase);
+            tma_phase ^= 1u;
+            {
+                const int tid = threadIdx.x;
+                constexpr int Q = P / 4;
+                const RawT* sa = stage;
+                const RawT* sb = stage + Cfg::RH * P;
+                for (int i = tid; i < Cfg::RH * Q; i += NT) {
+                    const int ly = i / Q, lq = i - ly * Q;
+                    float va[4], vb[4];
+                    if (sizeof(RawT) == 4) {
+                        const f4 xa = *reinterpret_cast<const f4*>(reinterpret_cast<const float*>(sa) + ly * P + 4 * lq);
+                        const f4 xb = *reinterpret_cast<const f4*>(reinterpret_cast<const float*>(sb) + ly * P + 4 * lq);
+                        va[0] = xa.x; va[1] = xa.y; va[2] = xa.z; va[3] = xa.w;
+                        vb[0] = xb.x; vb[1] = xb.y; vb[2] = xb.z; vb[3] = xb.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            va[j] = __fdiv_rn((float)sa[ly * P + 4 * lq + j], a.denom);
+                            vb[j] = __fdiv_rn((float)sb[ly * P + 4 * lq + j], a.denom);
+                        }
+                    }
+                    st4<P>(XR, ly * P + 2 * lq, mk2(va[0], vb[0]), mk2(va[1], vb[1]), mk2(va[2], vb[2]), mk2(va[3], vb[3]));
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int next = tile + n_cta;
+                if (next < grid.n) {
+                    int nb0, nb1, ny0, nx0;
+                    decode_pair_tile(grid, next, TH, TW, a.B, nb0, nb1, ny0, nx0);
+                    tma_load_3d(stage, tmap, nx0 - 8, ny0 - 4, nb0, mbar, kTmaBytes);
+                }
+            }
+            if (!interior) {
+                // the copy engine zero-fills outside the image; the demosaic needs the reflected 1-wide ring
+                const int tid = threadIdx.x;
+                for (int i = tid; i < 2 * P; i += NT) {
+                    const int gy = i < P ? -1 : H, lx = i < P ? i : i - P;
+                    const int ly = gy - (ty0 - 4), sy = mirror(gy, H) - (ty0 - 4);
+                    if (ly >= 0 && ly < Cfg::RH && sy >= 0 && sy < Cfg::RH) XR[ly * P + lx] = XR[sy * P + lx];
+                }
+                __syncthreads();
+                for (int i = tid; i < 2 * Cfg::RH; i += NT) {
+                    const int gx = i < Cfg::RH ? -1 : W, ly = i < Cfg::RH ? i : i - Cfg::RH;
+                    const int lx = gx - (tx0 - 8), sx = mirror(gx, W) - (tx0 - 8);
+                    if (lx >= 0 && lx < P && sx >= 0 && sx < P) XR[ly * P + phys<P>(lx)] = XR[ly * P + phys<P>(sx)];
+                }
+                __syncthreads();
+            }
+        } else
+#endif
         // ---- P1: raw window of both images -> XR (mirror-clamped indices; 4-site runs when fully inside) ----
         { R2L_FOR_THREADS(NT) {
             constexpr int Q = P / 4;                               // 4-site runs per row
             for (int i = tid; i < Cfg::RH * Q; i += NT) {
                 const int ly = i / Q, lq = i - ly * Q;
                 const int gy = ty0 - 4 + ly, gx = tx0 - 8 + 4 * lq;
-                f2* dst = XR + ly * P + 4 * lq;
+                const int eb = ly * P + 2 * lq;
                 if (vec_ok && sizeof(RawT) == 4 && gy >= 0 && gy < H && gx >= 0 && gx + 3 < W) {
                     const f4 va = *reinterpret_cast<const f4*>(reinterpret_cast<const float*>(imgA) + (size_t)gy * W + gx);
                     const f4 vb = *reinterpret_cast<const f4*>(reinterpret_cast<const float*>(imgB) + (size_t)gy * W + gx);
-                    st2(dst, mk2(va.x, vb.x), mk2(va.y, vb.y));
-                    st2(dst + 2, mk2(va.z, vb.z), mk2(va.w, vb.w));
+                    st4<P>(XR, eb, mk2(va.x, vb.x), mk2(va.y, vb.y), mk2(va.z, vb.z), mk2(va.w, vb.w));
                 } else {
                     const int sy = mirror_clamped(gy, H);
                     f2 v[4];
@@ -149,7 +265,7 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
                         v[j] = mk2(RawLoad<RawT>::get(imgA + (size_t)sy * W + sx, a.denom),
                                    RawLoad<RawT>::get(imgB + (size_t)sy * W + sx, a.denom));
                     }
-                    st2(dst, v[0], v[1]); st2(dst + 2, v[2], v[3]);
+                    st4<P>(XR, eb, v[0], v[1], v[2], v[3]);
                 }
             }
         } }
@@ -178,7 +294,7 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
             }
             for (int item = tid; item < TH * G; item += NT) {
                 const int r = item / G, g = item - r * G;
-                const int c = 8 + 4 * g;
+                const int q = 2 + g;                                  // run index: column index c = 8 + 4g = 4q
                 f2 acc[4][3];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -187,7 +303,7 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
 #pragma unroll
                 for (int aa = 0; aa < 3; ++aa) {
                     f2 in[6];
-                    ld6_odd(XR + (r + 3 + aa) * P + c - 1, in);
+                    ld6<P>(XR, (r + 3 + aa) * P + 2 * q, in);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -196,12 +312,9 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
                             for (int k = 0; k < 3; ++k)
                                 acc[j][k] = fma2s(in[j + bb], w[j & 1][k][aa * 3 + bb], acc[j][k]);
                 }
-                f2* y0p = Y0 + (r + 3) * P + c;
-                st2(y0p, acc[0][0], acc[1][0]); st2(y0p + 2, acc[2][0], acc[3][0]);
-                f2* up = U + r * TW + 4 * g;
-                st2(up, acc[0][1], acc[1][1]); st2(up + 2, acc[2][1], acc[3][1]);
-                f2* vp = V + r * TW + 4 * g;
-                st2(vp, acc[0][2], acc[1][2]); st2(vp + 2, acc[2][2], acc[3][2]);
+                st4<P>(Y0, (r + 3) * P + 2 * q, acc[0][0], acc[1][0], acc[2][0], acc[3][0]);
+                st4<TW>(U, r * TW + 2 * g, acc[0][1], acc[1][1], acc[2][1], acc[3][1]);
+                st4<TW>(V, r * TW + 2 * g, acc[0][2], acc[1][2], acc[2][2], acc[3][2]);
             }
             // halo items (luma only): 3 rows above/below x (G+2) groups, and the two side groups of every tile row
             constexpr int kTopBot = 6 * (G + 2), kSide = 2 * TH;
@@ -229,19 +342,18 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
                         for (int t = 0; t < 9; ++t) wy[cp][t] = tmp[cp * 9 + t];
                 }
                 const float cb0 = T2->cbrow[hp][0], cb1 = T2->cbrow[hp][3];
-                const int c = 8 + 4 * g;
+                const int q = 2 + g;
                 f2 acc[4] = {mk2(-cb0, -cb0), mk2(-cb1, -cb1), mk2(-cb0, -cb0), mk2(-cb1, -cb1)};
 #pragma unroll
                 for (int aa = 0; aa < 3; ++aa) {
                     f2 in[6];
-                    ld6_odd(XR + (ry + 3 + aa) * P + c - 1, in);
+                    ld6<P>(XR, (ry + 3 + aa) * P + 2 * q, in);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
 #pragma unroll
                         for (int bb = 0; bb < 3; ++bb) acc[j] = fma2s(in[j + bb], wy[j & 1][aa * 3 + bb], acc[j]);
                 }
-                f2* y0p = Y0 + (ry + 3) * P + c;
-                st2(y0p, acc[0], acc[1]); st2(y0p + 2, acc[2], acc[3]);
+                st4<P>(Y0, (ry + 3) * P + 2 * q, acc[0], acc[1], acc[2], acc[3]);
             }
         } }
         R2L_SYNC();
@@ -255,7 +367,7 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
                     else if (i < 2 * P + Cfg::Y0H) { gy = ty0 - 3 + (i - 2 * P); gx = -1; }
                     else { gy = ty0 - 3 + (i - 2 * P - Cfg::Y0H); gx = W; }
                     const int ly = gy - (ty0 - 3), lx = gx - (tx0 - 8);
-                    if (ly >= 0 && ly < Cfg::Y0H && lx >= 0 && lx < P) Y0[ly * P + lx] = mk2(0.f, 0.f);
+                    if (ly >= 0 && ly < Cfg::Y0H && lx >= 0 && lx < P) Y0[ly * P + phys<P>(lx)] = mk2(0.f, 0.f);
                 }
             } }
             R2L_SYNC();
@@ -268,19 +380,18 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
             for (int t = 0; t < 9; ++t) ws[t] = T->Ws[t];
             for (int item = tid; item < Cfg::Y1H * (G + 2); item += NT) {
                 const int rr = item / (G + 2), g = item - rr * (G + 2) - 1;
-                const int c = 8 + 4 * g;
+                const int q = 2 + g;
                 f2 acc[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
 #pragma unroll
                 for (int aa = 0; aa < 3; ++aa) {
                     f2 in[6];
-                    ld6_odd(Y0 + (rr + aa) * P + c - 1, in);      // Y1 row rr = image row ty0-2+rr; Y0 row of (that-1) is rr
+                    ld6<P>(Y0, (rr + aa) * P + 2 * q, in);        // Y1 row rr = image row ty0-2+rr; Y0 row of (that-1) is rr
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
 #pragma unroll
                         for (int bb = 0; bb < 3; ++bb) acc[j] = fma2s(in[j + bb], ws[aa * 3 + bb], acc[j]);
                 }
-                f2* y1p = Y1 + rr * P + c;
-                st2(y1p, acc[0], acc[1]); st2(y1p + 2, acc[2], acc[3]);
+                st4<P>(Y1, rr * P + 2 * q, acc[0], acc[1], acc[2], acc[3]);
             }
         } }
         R2L_SYNC();
@@ -291,7 +402,7 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
                     const int q = i / P, lx = i - q * P;
                     const int gy = q == 0 ? -2 : (q == 1 ? -1 : (q == 2 ? H : H + 1));
                     const int ly = gy - (ty0 - 2), sy = mirror(gy, H) - (ty0 - 2);
-                    if (ly >= 0 && ly < Cfg::Y1H && sy >= 0 && sy < Cfg::Y1H) Y1[ly * P + lx] = Y1[sy * P + lx];
+                    if (ly >= 0 && ly < Cfg::Y1H && sy >= 0 && sy < Cfg::Y1H) Y1[ly * P + lx] = Y1[sy * P + lx];   // same physical column
                 }
             } }
             R2L_SYNC();
@@ -300,7 +411,7 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
                     const int q = i / Cfg::Y1H, ly = i - q * Cfg::Y1H;
                     const int gx = q == 0 ? -2 : (q == 1 ? -1 : (q == 2 ? W : W + 1));
                     const int lx = gx - (tx0 - 8), sx = mirror(gx, W) - (tx0 - 8);
-                    if (lx >= 0 && lx < P && sx >= 0 && sx < P) Y1[ly * P + lx] = Y1[ly * P + sx];
+                    if (lx >= 0 && lx < P && sx >= 0 && sx < P) Y1[ly * P + phys<P>(lx)] = Y1[ly * P + phys<P>(sx)];
                 }
             } }
             R2L_SYNC();
@@ -316,7 +427,7 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
             const float invg = T->invg;
             for (int item = tid; item < (TH / 2) * G; item += NT) {
                 const int r0 = 2 * (item / G), g = item % G;
-                const int c = 8 + 4 * g;
+                const int q = 2 + g;
                 f2 acc[2][4];
 #pragma unroll
                 for (int o = 0; o < 2; ++o)
@@ -325,7 +436,7 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
 #pragma unroll
                 for (int ir = 0; ir < 6; ++ir) {
                     f2 in[8];
-                    ld8_even(Y1 + (r0 + ir) * P + c - 2, in);     // Y1 row index of image row (ty0 + r0 - 2 + ir)
+                    ld8<P>(Y1, (r0 + ir) * P + 2 * q, in);        // Y1 row index of image row (ty0 + r0 - 2 + ir)
 #pragma unroll
                     for (int o = 0; o < 2; ++o) {
                         const int aa = ir - o;
@@ -342,8 +453,8 @@ R2L_HD void fwd2_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
                     const int gy = ty0 + r0 + o, gx = tx0 + 4 * g;
                     if (gy >= H || gx >= W) continue;
                     f2 u[4], v[4];
-                    ld2(U + (r0 + o) * TW + 4 * g, u[0], u[1]); ld2(U + (r0 + o) * TW + 4 * g + 2, u[2], u[3]);
-                    ld2(V + (r0 + o) * TW + 4 * g, v[0], v[1]); ld2(V + (r0 + o) * TW + 4 * g + 2, v[2], v[3]);
+                    ld4<TW>(U, (r0 + o) * TW + 2 * g, u);
+                    ld4<TW>(V, (r0 + o) * TW + 2 * g, v);
                     float oa[3][4], ob[3][4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j)

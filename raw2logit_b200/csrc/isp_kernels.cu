@@ -3,8 +3,10 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC  (see _build.py)
 // No torch headers, no host-side state: every call validates its arguments, enqueues kernels on the caller's
 // stream and returns.
+#include <cuda.h>            // CUtensorMap types only; the encoder is fetched through the runtime (no libcuda link)
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/r2l_isp.h"
 #include "isp_config.h"
@@ -16,8 +18,15 @@ namespace r2l {
 // ---------------------------------------------------------------------------------------------------------
 template <class Cfg, typename RawT, bool STATS>
 __global__ void __launch_bounds__(Cfg::NT, 2) isp_forward_kernel(FwdArgs a, TileGrid grid) {
-    extern __shared__ __align__(16) float smem[];
-    fwd2_cta<Cfg, RawT, STATS>(blockIdx.x, gridDim.x, a, grid, smem);
+    extern __shared__ __align__(128) float smem[];
+    fwd2_cta<Cfg, RawT, STATS, false>(blockIdx.x, gridDim.x, a, grid, smem);
+}
+// same kernel, raw window delivered by TMA (tensor map over raw as (W, H, B))
+template <class Cfg, typename RawT, bool STATS>
+__global__ void __launch_bounds__(Cfg::NT, 2) isp_forward_tma_kernel(FwdArgs a, TileGrid grid,
+                                                                     const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float smem[];
+    fwd2_cta<Cfg, RawT, STATS, true>(blockIdx.x, gridDim.x, a, grid, smem, &tmap);
 }
 
 // ---- train-mode BatchNorm2d(3, affine=False) tail (pipeline_torch.py:168, 216-217) -------------------------
@@ -107,7 +116,7 @@ __global__ void bn_backward_finish_kernel(const float* partials, const float* af
 
 template <class Cfg, typename RawT>
 __global__ void __launch_bounds__(Cfg::NT) isp_backward_kernel(BwdArgs a, TileGrid grid) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     bwd_cta<Cfg, RawT>(blockIdx.x, gridDim.x, a, grid, smem);
 }
 
@@ -240,13 +249,54 @@ static int persistent_grid(K kernel, int threads, size_t smem, int n_tiles, int*
     return R2L_OK;
 }
 
+// ---- tensor map over the raw batch: dims (W, H, B), box (box_w, box_h, 2), zero fill outside ---------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// false when the shape/pointer does not meet TMA's 16-byte rules (then the generic loader runs)
+static bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_bytes, int B, int H, int W, int box_w,
+                                int box_h) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    if (const char* off = getenv("R2L_ISP_NO_TMA")) {          // debugging knob: force the generic loader
+        if (off[0] == '1') return false;
+    }
+    if ((reinterpret_cast<uintptr_t>(raw) & 15) || ((size_t)W * elem_bytes) % 16 != 0) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t gstride[2] = {(cuuint64_t)W * elem_bytes, (cuuint64_t)W * H * elem_bytes};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 2u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+    return fn(map, dt, 3, const_cast<void*>(raw), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <class Cfg, typename RawT, bool STATS>
 static int launch_forward(const FwdArgs& a, cudaStream_t st, int* grid_used = nullptr) {
     const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);     // tiles of image pairs
     int g = 0;
-    int rc = persistent_grid(isp_forward_kernel<Cfg, RawT, STATS>, Cfg::NT, Cfg::kSmemBytes, grid.n, &g);
-    if (rc != R2L_OK) return rc;
-    isp_forward_kernel<Cfg, RawT, STATS><<<g, Cfg::NT, Cfg::kSmemBytes, st>>>(a, grid);
+    CUtensorMap tmap;
+    if (make_raw_tensor_map(&tmap, a.raw, (int)sizeof(RawT), a.B, a.H, a.W, Cfg::P, Cfg::RH)) {
+        int rc = persistent_grid(isp_forward_tma_kernel<Cfg, RawT, STATS>, Cfg::NT, Cfg::kSmemBytesTma, grid.n, &g);
+        if (rc != R2L_OK) return rc;
+        isp_forward_tma_kernel<Cfg, RawT, STATS><<<g, Cfg::NT, Cfg::kSmemBytesTma, st>>>(a, grid, tmap);
+    } else {
+        int rc = persistent_grid(isp_forward_kernel<Cfg, RawT, STATS>, Cfg::NT, Cfg::kSmemBytes, grid.n, &g);
+        if (rc != R2L_OK) return rc;
+        isp_forward_kernel<Cfg, RawT, STATS><<<g, Cfg::NT, Cfg::kSmemBytes, st>>>(a, grid);
+    }
     if (grid_used) *grid_used = g;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);

@@ -235,3 +235,25 @@ def test_frozen_processor_runs_forward_only():
     out = mod(syn.smooth_scene(2, 64, 64).cuda())
     assert not out.requires_grad and out.shape == (2, 3, 64, 64)
     assert mod.buffer["processed_rgb"] is out
+
+
+def test_tma_loader_and_generic_loader_agree_bitwise():
+    """Aligned shapes take the TMA staging path (UTMALDG + mbarrier); R2L_ISP_NO_TMA=1 forces the generic loader."""
+    import os
+    state = syn.perturbed_state(isp_oracle.default_state(syn.CAMERA_PRESETS["drone"]))
+    mod = _module(state)
+    for shape in [(5, 256, 256), (2, 96, 200), (1, 40, 8), (3, 1024, 512)]:
+        raw = syn.smooth_scene(*shape, "drone", seed=21).cuda()
+        u16 = syn.to_uint16(raw.cpu()).cuda() if shape[2] % 8 == 0 else None
+        with torch.no_grad():
+            a = mod(raw)
+            au = mod(u16) if u16 is not None else None
+            os.environ["R2L_ISP_NO_TMA"] = "1"
+            try:
+                b = mod(raw)
+                bu = mod(u16) if u16 is not None else None
+            finally:
+                os.environ["R2L_ISP_NO_TMA"] = "0"
+        assert torch.equal(a, b), shape
+        if au is not None:
+            assert torch.equal(au, bu), shape
