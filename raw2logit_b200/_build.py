@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libr2l_isp.so")
 SOURCES = [os.path.join(CSRC, "isp_kernels.cu")]
-HEADERS = [os.path.join(CSRC, "isp_core.cuh"), os.path.join(CSRC, "isp_fwd2.cuh"), os.path.join(CSRC, "isp_config.h"),
+HEADERS = [os.path.join(CSRC, "isp_core.cuh"), os.path.join(CSRC, "isp_fwd2.cuh"), os.path.join(CSRC, "isp_bwd2.cuh"), os.path.join(CSRC, "isp_config.h"),
            os.path.join(ROOT, "include", "r2l_isp.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -2,11 +2,14 @@
 #pragma once
 #include "isp_core.cuh"
 #include "isp_fwd2.cuh"
+#include "isp_bwd2.cuh"
 
 namespace r2l {
 using FwdDefault = FwdCfg<32, 64, 256>;          // v1 (scalar) -- kept for the emulation cross-check only
 using Fwd2Default = Fwd2Cfg<32, 64, 256>;        // v2: image pairs, FFMA2, register micro-tiles
-using BwdNoRaw = BwdCfg<32, 64, 256, false>;
+using BwdNoRaw = BwdCfg<32, 64, 256, false>;     // v1 (scalar) -- emulation cross-check only
+using Bwd2NoRaw = Bwd2Cfg<32, 64, 256, false>;
+using Bwd2WithRaw = Bwd2Cfg<32, 64, 256, true>;
 using BwdWithRaw = BwdCfg<32, 64, 256, true>;
 constexpr int kMaxCtas = 2048;          // upper bound on persistent CTAs == rows of the statistics workspace
 }  // namespace r2l

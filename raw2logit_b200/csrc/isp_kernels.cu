@@ -115,9 +115,15 @@ __global__ void bn_backward_finish_kernel(const float* partials, const float* af
 }
 
 template <class Cfg, typename RawT>
-__global__ void __launch_bounds__(Cfg::NT) isp_backward_kernel(BwdArgs a, TileGrid grid) {
+__global__ void __launch_bounds__(Cfg::NT, 1) isp_backward_kernel(BwdArgs a, TileGrid grid) {
     extern __shared__ __align__(128) float smem[];
-    bwd_cta<Cfg, RawT>(blockIdx.x, gridDim.x, a, grid, smem);
+    bwd2_cta<Cfg, RawT, false>(blockIdx.x, gridDim.x, a, grid, smem);
+}
+template <class Cfg, typename RawT>
+__global__ void __launch_bounds__(Cfg::NT, 1) isp_backward_tma_kernel(BwdArgs a, TileGrid grid,
+                                                                      const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float smem[];
+    bwd2_cta<Cfg, RawT, true>(blockIdx.x, gridDim.x, a, grid, smem, &tmap);
 }
 
 // statistics of all CTAs -> 132 parameter gradients.  One CTA; sums over CTAs in double, in a fixed order.
@@ -304,11 +310,18 @@ static int launch_forward(const FwdArgs& a, cudaStream_t st, int* grid_used = nu
 
 template <class Cfg, typename RawT>
 static int launch_backward(const BwdArgs& a, float* grads, cudaStream_t st) {
-    const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
+    const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);     // tiles of image pairs
     int g = 0;
-    int rc = persistent_grid(isp_backward_kernel<Cfg, RawT>, Cfg::NT, Cfg::kSmemBytes, grid.n, &g);
-    if (rc != R2L_OK) return rc;
-    isp_backward_kernel<Cfg, RawT><<<g, Cfg::NT, Cfg::kSmemBytes, st>>>(a, grid);
+    CUtensorMap tmap;
+    if (make_raw_tensor_map(&tmap, a.raw, (int)sizeof(RawT), a.B, a.H, a.W, Cfg::PW, Cfg::RH)) {
+        int rc = persistent_grid(isp_backward_tma_kernel<Cfg, RawT>, Cfg::NT, Cfg::kSmemBytesTma, grid.n, &g);
+        if (rc != R2L_OK) return rc;
+        isp_backward_tma_kernel<Cfg, RawT><<<g, Cfg::NT, Cfg::kSmemBytesTma, st>>>(a, grid, tmap);
+    } else {
+        int rc = persistent_grid(isp_backward_kernel<Cfg, RawT>, Cfg::NT, Cfg::kSmemBytes, grid.n, &g);
+        if (rc != R2L_OK) return rc;
+        isp_backward_kernel<Cfg, RawT><<<g, Cfg::NT, Cfg::kSmemBytes, st>>>(a, grid);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
     isp_backward_finish_kernel<<<1, kFinishThreads, 0, st>>>(a.P, a.partials, g, grads);
@@ -425,11 +438,11 @@ int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int 
     a.raw = raw; a.denom = raw_denominator; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.gout = grad_out; a.gtail = grad_tail; a.additive = additive; a.graw = grad_raw; a.partials = static_cast<float*>(workspace);
     if (grad_raw) {
-        return raw_dtype == R2L_F32 ? launch_backward<BwdWithRaw, float>(a, grad_params, st)
-                                    : launch_backward<BwdWithRaw, uint16_t>(a, grad_params, st);
+        return raw_dtype == R2L_F32 ? launch_backward<Bwd2WithRaw, float>(a, grad_params, st)
+                                    : launch_backward<Bwd2WithRaw, uint16_t>(a, grad_params, st);
     }
-    return raw_dtype == R2L_F32 ? launch_backward<BwdNoRaw, float>(a, grad_params, st)
-                                : launch_backward<BwdNoRaw, uint16_t>(a, grad_params, st);
+    return raw_dtype == R2L_F32 ? launch_backward<Bwd2NoRaw, float>(a, grad_params, st)
+                                : launch_backward<Bwd2NoRaw, uint16_t>(a, grad_params, st);
 }
 
 int r2l_isp_mosaic(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,

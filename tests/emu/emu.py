@@ -11,6 +11,7 @@ SRC = os.path.join(HERE, "isp_emu.cpp")
 LIB = os.path.join(HERE, "libisp_emu.so")
 DEPS = [SRC, os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_core.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_fwd2.cuh"),
+        os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd2.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_config.h"), os.path.join(ROOT, "include", "r2l_isp.h")]
 
 PARAM_FIELDS = ["black_level", "white_balance", "colour_correction", "gamma_correct", "debayer.weight",
@@ -73,7 +74,8 @@ def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0, vers
     return out
 
 
-def backward(raw, state, grad_out, need_raw_grad=True, n_cta=3, denom=65535.0, grad_tail=None, additive=None):
+def backward(raw, state, grad_out, need_raw_grad=True, n_cta=3, denom=65535.0, grad_tail=None, additive=None,
+             version=2):
     raw = np.ascontiguousarray(raw)
     dtype = 1 if raw.dtype == np.uint16 else 0
     if dtype == 0:
@@ -90,7 +92,7 @@ def backward(raw, state, grad_out, need_raw_grad=True, n_cta=3, denom=65535.0, g
                                 None if gs is None else ctypes.c_void_p(gs.ctypes.data),
                                 None if add is None else ctypes.c_void_p(add.ctypes.data),
                                 None if graw is None else ctypes.c_void_p(graw.ctypes.data),
-                                ctypes.c_void_p(gpar.ctypes.data), n_cta)
+                                ctypes.c_void_p(gpar.ctypes.data), n_cta, version)
     assert rc == 0, rc
     grads = {k: gpar[a:b_] for k, (a, b_) in GRAD_SLICES.items()}
     if graw is not None:

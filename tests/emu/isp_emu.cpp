@@ -36,10 +36,19 @@ static void run_forward(const FwdArgs& a, int n_cta) {
 }
 
 template <class Cfg, typename RawT>
-static void run_backward(const BwdArgs& a, int n_cta, float* grads) {
-    const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
-    std::vector<float> smem(Cfg::kSmemFloats);
-    for (int cta = 0; cta < n_cta; ++cta) bwd_cta<Cfg, RawT>(cta, n_cta, a, grid, smem.data());
+static void run_backward(const BwdArgs& a, int n_cta, float* grads, int version) {
+    if (version == 1) {
+        const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
+        std::vector<float> smem(Cfg::kSmemFloats);
+        for (int cta = 0; cta < n_cta; ++cta) bwd_cta<Cfg, RawT>(cta, n_cta, a, grid, smem.data());
+    } else {
+        using C2 = Bwd2Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW>;
+        const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, C2::TH, C2::TW);
+        std::vector<float> smem(C2::kSmemBytes / 4 + 4);
+        float* base = smem.data();
+        while (reinterpret_cast<uintptr_t>(base) % 16) ++base;
+        for (int cta = 0; cta < n_cta; ++cta) bwd2_cta<C2, RawT, false>(cta, n_cta, a, grid, base);
+    }
     // finish (same arithmetic as isp_backward_finish_kernel)
     std::vector<float> tmem((sizeof(Tables) + 3) / 4);
     Tables* T = reinterpret_cast<Tables*>(tmem.data());
@@ -85,18 +94,18 @@ int emu_isp_forward(const void* raw, int raw_dtype, float denom, int B, int H, i
 
 int emu_isp_backward(const void* raw, int raw_dtype, float denom, int B, int H, int W, const r2l_isp_params* params,
                      const float* grad_out, const float* grad_tail, const float* additive, float* grad_raw,
-                     float* grad_params, int n_cta) {
+                     float* grad_params, int n_cta, int version) {
     if (H < 3 || W < 3) return R2L_ERR_BAD_SHAPE;
     std::vector<float> partials((size_t)n_cta * kStatPitch, 0.f);
     BwdArgs a;
     a.raw = raw; a.denom = denom; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.gout = grad_out; a.gtail = grad_tail; a.additive = additive; a.graw = grad_raw; a.partials = partials.data();
     if (grad_raw) {
-        if (raw_dtype == R2L_F32) run_backward<BwdWithRaw, float>(a, n_cta, grad_params);
-        else run_backward<BwdWithRaw, uint16_t>(a, n_cta, grad_params);
+        if (raw_dtype == R2L_F32) run_backward<BwdWithRaw, float>(a, n_cta, grad_params, version);
+        else run_backward<BwdWithRaw, uint16_t>(a, n_cta, grad_params, version);
     } else {
-        if (raw_dtype == R2L_F32) run_backward<BwdNoRaw, float>(a, n_cta, grad_params);
-        else run_backward<BwdNoRaw, uint16_t>(a, n_cta, grad_params);
+        if (raw_dtype == R2L_F32) run_backward<BwdNoRaw, float>(a, n_cta, grad_params, version);
+        else run_backward<BwdNoRaw, uint16_t>(a, n_cta, grad_params, version);
     }
     return R2L_OK;
 }
