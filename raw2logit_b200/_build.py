@@ -1,17 +1,30 @@
-"""Builds the CUDA library in-tree: raw2logit_b200/libr2l_isp.so (sm_100a only, no torch headers involved)."""
+"""Builds the CUDA library in-tree: raw2logit_b200/libr2l_isp.so (sm_100a only, no torch headers involved).
+
+Every csrc/*.cu is its own translation unit (forward / backward per raw element type, generic kernels, host ABI);
+they are compiled in parallel to objects under csrc/_obj/ and linked with `nvcc -shared`.
+"""
+import glob
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIB_PATH = os.path.join(HERE, "libr2l_isp.so")
-SOURCES = [os.path.join(CSRC, "isp_kernels.cu")]
-HEADERS = [os.path.join(CSRC, "isp_core.cuh"), os.path.join(CSRC, "isp_fwd2.cuh"), os.path.join(CSRC, "isp_bwd2.cuh"), os.path.join(CSRC, "isp_config.h"),
-           os.path.join(ROOT, "include", "r2l_isp.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def headers():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
+                  [os.path.join(ROOT, "include", "r2l_isp.h")])
 
 
 def nvcc_path():
@@ -25,20 +38,44 @@ def is_stale():
     if not os.path.exists(LIB_PATH):
         return True
     built = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS)
+    return any(os.path.getmtime(p) > built for p in sources() + headers())
+
+
+def _obj_path(src):
+    return os.path.join(OBJ, os.path.splitext(os.path.basename(src))[0] + ".o")
+
+
+def _compile_one(src, verbose):
+    obj = _obj_path(src)
+    newest_dep = max(os.path.getmtime(p) for p in [src] + headers())
+    if os.path.exists(obj) and os.path.getmtime(obj) >= newest_dep:
+        return src, ""
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+    return src, res.stderr
 
 
 def build(force=False, verbose=False):
     """Compile csrc/*.cu for sm_100a into libr2l_isp.so next to this file.  Returns the library path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH + ".tmp"] + SOURCES
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for o in glob.glob(os.path.join(OBJ, "*.o")):
+            os.remove(o)
+    srcs = sources()
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
+        logs = list(pool.map(lambda s: _compile_one(s, verbose), srcs))
+    cmd = [nvcc_path()] + ARCH_FLAGS + ["-shared", "-o", LIB_PATH + ".tmp"] + [_obj_path(s) for s in srcs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
     if verbose:
-        print(res.stderr)
+        for src, log in logs:
+            print(f"== {os.path.basename(src)}\n{log}")
     return LIB_PATH
 
 

@@ -1,0 +1,671 @@
+// isp_bwd3.cuh -- third-generation fused backward: branch-free phases over padded domains.
+//
+// Reference: the autograd graph of pipeline_torch.py:183-217.  Same adjoint algebra and the same
+// float2 (image A, image B) planes / FFMA2 arithmetic as the second generation, but the schedule is rebuilt around
+// what its profile showed (profiles/r02_v2_summary.md: FFMA2 was 19 % of the issued instructions, the rest was
+// border slow paths, index arithmetic and instruction-cache misses of a 29 k-instruction kernel):
+//   * every stencil loop is branch-free.  Border rules are realised on the DATA, not in the loops:
+//       - the raw window is mirrored while it is de-interleaved into the plane (reflect-1 of the mosaic);
+//       - Y0 is stored as exact zeros outside the image (the sharpen conv zero-pads, and every statistic that
+//         multiplies Y0 or a gradient plane by a neighbour is then automatically restricted to the image);
+//       - Y1 pad rows are computed at the mirrored row, pad columns are written by the run that owns the mirror
+//         source (Gaussian reflect-2 of the sharpened plane);
+//       - grad_out is read as zero outside the image, so gY2/gU/gV vanish there;
+//       - adjoints are evaluated on the padded domain and the pad sites are folded onto their mirror targets by one
+//         small gather pass (only tiles that touch the image border run it);
+//   * work items are 1x4 site runs that are entirely inside or entirely outside the image (needs W % 4 == 0; other
+//     shapes take the generic scalar kernel), so "inside the image" is one predicate per item;
+//   * threads are split by warp parity into the two CFA row phases, so the phase-bound weights (B2) and
+//     statistics (B7) stay in registers for every tile of the persistent CTA, with a uniform item count per warp;
+//   * statistics are accumulated next to the adjoint gathers (flipped form, see isp_bwd2.cuh) with run-level
+//     predicates only.
+// Shapes the fold pass cannot serve from one tile (a last tile row/column of <= 4 sites) go to the generic kernel.
+#pragma once
+#include "isp_fwd2.cuh"
+
+namespace r2l {
+
+template <int P> R2L_HD f2& site3(f2* pl, int row, int col) { return pl[row * P + phys<P>(col)]; }
+R2L_HD f2 add2v(f2 a, f2 b) { return mk2(a.x + b.x, a.y + b.y); }
+R2L_HD f2 fma2vv(f2 a, f2 b, f2 c) {
+#ifdef R2L_HOST_EMU
+    return mk2(std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y));
+#else
+    return __ffma2_rn(a, b, c);
+#endif
+}
+R2L_HD f2 mul2vv(f2 a, f2 b) {
+#ifdef R2L_HOST_EMU
+    return mk2(a.x * b.x, a.y * b.y);
+#else
+    return __fmul2_rn(a, b);
+#endif
+}
+
+struct Bwd3Acc {
+    f2 sg;               // sum G o log2(cl), per stream
+    float wg[25];        // flipped Gaussian-weight statistic
+    float ws[9];         // flipped sharpen-weight statistic
+    float q[2][3][9];    // Q'[col phase of q][k][t] for this thread's row phase
+    float p[2][3];       // P[col phase][k] = sum g_yuv[k](q) over owned sites
+};
+constexpr int kBwd3AccFloats = 2 + 25 + 9 + 54 + 6;
+
+// reflect-pad pre-images (isp_core.cuh: preimages1 / preimages2) are reused for the fold passes
+
+template <int TH_, int TW_, int NT_, bool GRAW_, bool TAIL_> struct Bwd3Cfg {
+    static constexpr int TH = TH_, TW = TW_, NT = NT_;
+    static constexpr bool GRAW = GRAW_, TAIL = TAIL_;
+    static constexpr int G = TW / 4;
+    static constexpr int PW = TW + 24;        // wide planes (raw, Y0, Y1): column index = gx - x0 + 12, run q = g + 3
+    static constexpr int PN = TW + 16;        // narrow planes (F, gY1):    column index = gx - x0 + 8,  run q = g + 2
+    static constexpr int RH = TH + 16, Y0H = TH + 14, Y1H = TH + 12, FH = TH + 8, G1H = TH + 4;
+    static constexpr int kTableFloats = (sizeof(Tables2) + 15) / 16 * 4;
+    static constexpr int kXR = RH * PW, kY0 = Y0H * PW, kF = FH * PN, kG1 = G1H * PN;
+    static constexpr int kSites = kXR + kY0 + 3 * kF + kG1;
+    static constexpr size_t kPlaneBytes = (size_t)kTableFloats * 4 + (size_t)kSites * 8;
+    static constexpr size_t kStageOffset = (kPlaneBytes + 127) / 128 * 128;
+    static constexpr size_t kStageBytes = (size_t)2 * RH * PW * 4;
+    static constexpr size_t kSmemBytes = kPlaneBytes;
+    static constexpr size_t kSmemBytesTma = kStageOffset + kStageBytes + 16;
+    static constexpr int HALF = NT / 2;       // threads per CFA row phase
+    static_assert(NT % 64 == 0 && TH % 2 == 0 && TW % 8 == 0, "warp-parity mapping");
+    static_assert(Y1H * PW <= kXR, "Y1 aliases the raw window");
+    static_assert((size_t)NT * (kBwd3AccFloats + 1) * 4 <= (size_t)kSites * 8, "reduction scratch");
+};
+
+// shapes the third generation serves (the rest goes to the generic scalar kernel)
+inline bool bwd3_shape_ok(int H, int W, int TH, int TW) {
+    const int rh = H % TH, rw = W % TW;
+    return (W % 4) == 0 && H >= 8 && W >= 8 && (rh == 0 || rh > 4) && (rw == 0 || rw > 4);
+}
+
+template <class Cfg, typename RawT, bool TMA = false>
+R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid, float* smem, const void* tmap = nullptr) {
+    constexpr int TH = Cfg::TH, TW = Cfg::TW, NT = Cfg::NT, PW = Cfg::PW, PN = Cfg::PN, G = Cfg::G, HALF = Cfg::HALF;
+    constexpr int GG = G + 2;                                     // runs -1 .. G
+    Tables2* T2 = reinterpret_cast<Tables2*>(smem);
+    Tables* T = &T2->base;
+    f2* XR = reinterpret_cast<f2*>(smem + Cfg::kTableFloats);     // raw window, later Y1
+    f2* Y0 = XR + Cfg::kXR;
+    f2* PU = Y0 + Cfg::kY0;                                       // U, then gU
+    f2* PV = PU + Cfg::kF;                                        // V, then gV
+    f2* PG = PV + Cfg::kF;                                        // gY2, then gY0
+    f2* GY1 = PG + Cfg::kF;                                       // gY1, then the padded g_raw
+    f2* Y1 = XR;
+#ifdef R2L_HOST_EMU
+    std::vector<Bwd3Acc> accs(NT);
+    std::memset(accs.data(), 0, sizeof(Bwd3Acc) * NT);
+#else
+    Bwd3Acc accs;
+    {
+        float* z = reinterpret_cast<float*>(&accs);
+#pragma unroll
+        for (int i = 0; i < kBwd3AccFloats; ++i) z[i] = 0.f;
+    }
+#endif
+    // planes start finite: never-written pad columns and out-of-image sites are read by don't-care items
+    { R2L_FOR_THREADS(NT) {
+        for (int i = tid; i < Cfg::kSites; i += NT) XR[i] = mk2(0.f, 0.f);
+    } }
+    R2L_BUILD_TABLES(NT, a.P, T)
+    { R2L_FOR_THREADS(NT) { build_tables2_extra(tid, NT, T2); } }
+    R2L_SYNC();
+
+    const int H = a.H, W = a.W;
+    const size_t plane = (size_t)H * W;
+#ifndef R2L_HOST_EMU
+    RawT* stage = reinterpret_cast<RawT*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset + Cfg::kStageBytes);
+    uint32_t tma_phase = 0;
+    constexpr uint32_t kTmaBytes = 2u * Cfg::RH * PW * sizeof(RawT);
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(mbar, 1);
+            if (cta < grid.n) {
+                int pb0, pb1, py0, px0;
+                decode_pair_tile(grid, cta, TH, TW, a.B, pb0, pb1, py0, px0);
+                tma_load_3d(stage, tmap, px0 - 12, py0 - 8, pb0, mbar, kTmaBytes);
+            }
+        }
+        __syncthreads();
+    }
+#endif
+    for (int tile = cta; tile < grid.n; tile += n_cta) {
+        int b0, b1, ty0, tx0;
+        decode_pair_tile(grid, tile, TH, TW, a.B, b0, b1, ty0, tx0);
+        const bool dup = b1 == b0;
+        const RawT* imgA = static_cast<const RawT*>(a.raw) + (size_t)b0 * plane;
+        const RawT* imgB = static_cast<const RawT*>(a.raw) + (size_t)b1 * plane;
+        const int e_top = ty0 == 0, e_bot = ty0 + TH >= H, e_lft = tx0 == 0, e_rgt = tx0 + TW >= W;
+        const bool border = e_top | e_bot | e_lft | e_rgt;
+
+#ifndef R2L_HOST_EMU
+        if (TMA) {
+            mbar_wait(mbar, tma_phase);      // this tile's raw window has landed in the staging buffer
+            tma_phase ^= 1u;
+        }
+#endif
+        // ---- B1: raw window (rows -8..TH+7, runs -3..G+2) de-interleaved into float2 sites, mirrored --------------
+        // Runs outside the image are never stored; the run that starts at column 0 also writes pad column -1
+        // (= column 1) and the run that ends at column W-1 writes pad column W (= column W-2).  Pad rows read the
+        // mirrored source row.
+        { R2L_FOR_THREADS(NT) {
+            constexpr int Q = PW / 4;
+            for (int i = tid; i < Cfg::RH * Q; i += NT) {
+                const int ly = i / Q, lq = i - ly * Q;
+                const int gy = ty0 - 8 + ly, gx = tx0 - 12 + 4 * lq;
+                if (gx < 0 || gx >= W) continue;
+                const int sy = mirror_clamped(gy, H);
+                float va[4], vb[4];
+#ifndef R2L_HOST_EMU
+                if (TMA) {
+                    const int sl = imin(imax(sy - (ty0 - 8), 0), Cfg::RH - 1);
+                    const RawT* sa = stage + sl * PW + 4 * lq;
+                    const RawT* sb = sa + Cfg::RH * PW;
+                    if (sizeof(RawT) == 4) {
+                        const f4 xa = *reinterpret_cast<const f4*>(sa);
+                        const f4 xb = *reinterpret_cast<const f4*>(sb);
+                        va[0] = xa.x; va[1] = xa.y; va[2] = xa.z; va[3] = xa.w;
+                        vb[0] = xb.x; vb[1] = xb.y; vb[2] = xb.z; vb[3] = xb.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            va[j] = __fdiv_rn((float)sa[j], a.denom);
+                            vb[j] = __fdiv_rn((float)sb[j], a.denom);
+                        }
+                    }
+                } else
+#endif
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        va[j] = RawLoad<RawT>::get(imgA + (size_t)sy * W + gx + j, a.denom);
+                        vb[j] = RawLoad<RawT>::get(imgB + (size_t)sy * W + gx + j, a.denom);
+                    }
+                }
+                st4<PW>(XR, ly * PW + 2 * lq, mk2(va[0], vb[0]), mk2(va[1], vb[1]), mk2(va[2], vb[2]), mk2(va[3], vb[3]));
+                if (gx == 0 && lq > 0) site3<PW>(XR, ly, 4 * lq - 1) = mk2(va[1], vb[1]);
+                if (gx + 4 == W && lq < Q - 1) site3<PW>(XR, ly, 4 * lq + 4) = mk2(va[2], vb[2]);
+            }
+        } }
+        R2L_SYNC();
+#ifndef R2L_HOST_EMU
+        if (TMA && threadIdx.x == 0) {
+            const int next = tile + n_cta;
+            if (next < grid.n) {
+                int nb0, nb1, ny0, nx0;
+                decode_pair_tile(grid, next, TH, TW, a.B, nb0, nb1, ny0, nx0);
+                tma_load_3d(stage, tmap, nx0 - 12, ny0 - 8, nb0, mbar, kTmaBytes);
+            }
+        }
+#endif
+
+        // ---- B2: Y0 (exact zero outside the image) on rows -7..TH+6; U,V on the F region (rows -4..TH+3, runs -1..G)
+        { R2L_FOR_THREADS(NT) {
+            const int rp = (tid >> 5) & 1, slot = ((tid >> 6) << 5) | (tid & 31);
+            float w[2][3][9], cb[2][3];
+            {
+                const f4* src = reinterpret_cast<const f4*>(T2->awrow[rp]);
+                float tmp[56];
+#pragma unroll
+                for (int q = 0; q < 14; ++q) { const f4 v = src[q]; tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w; }
+#pragma unroll
+                for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) w[cp][k][t] = tmp[cp * 27 + k * 9 + t];
+#pragma unroll
+                for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) cb[cp][k] = T2->cbrow[rp][cp * 3 + k];
+            }
+            // rows -4+rp, -2+rp, ... of this thread's phase: (TH+8)/2 rows x GG runs
+            for (int i = slot; i < (Cfg::FH / 2) * GG; i += HALF) {
+                const int ri = i / GG, g = i - ri * GG - 1;
+                const int r = -4 + rp + 2 * ri;
+                f2 acc[4][3];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) acc[j][k] = mk2(-cb[j & 1][k], -cb[j & 1][k]);
+#pragma unroll
+                for (int aa = 0; aa < 3; ++aa) {
+                    f2 in[6];
+                    ld6<PW>(XR, (r + 7 + aa) * PW + 2 * (g + 3), in);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+                            for (int k = 0; k < 3; ++k)
+                                acc[j][k] = fma2s(in[j + bb], w[j & 1][k][aa * 3 + bb], acc[j][k]);
+                }
+                const int gy = ty0 + r, gx = tx0 + 4 * g;
+                if (gy < 0 || gy >= H || gx < 0 || gx >= W) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j][0] = mk2(0.f, 0.f);
+                }
+                st4<PW>(Y0, (r + 7) * PW + 2 * (g + 3), acc[0][0], acc[1][0], acc[2][0], acc[3][0]);
+                st4<PN>(PU, (r + 4) * PN + 2 * (g + 2), acc[0][1], acc[1][1], acc[2][1], acc[3][1]);
+                st4<PN>(PV, (r + 4) * PN + 2 * (g + 2), acc[0][2], acc[1][2], acc[2][2], acc[3][2]);
+            }
+        } }
+        // luma-only ring: rows -7..-5 and TH+4..TH+6 x runs -2..G+1, plus runs -2 and G+1 of the F rows
+        { R2L_FOR_THREADS(NT) {
+            constexpr int kTopBot = 6 * (G + 4), kSide = 2 * (TH + 8);
+            for (int item = tid; item < kTopBot + kSide; item += NT) {
+                int ry, g;
+                if (item < kTopBot) {
+                    const int rr = item / (G + 4);
+                    g = item - rr * (G + 4) - 2;
+                    ry = rr < 3 ? rr - 7 : TH + 4 + (rr - 3);
+                } else {
+                    const int s = item - kTopBot;
+                    ry = (s >> 1) - 4;
+                    g = (s & 1) ? G + 1 : -2;
+                }
+                const int hp = ry & 1;
+                float wy[2][9];
+                {
+                    const f4* src = reinterpret_cast<const f4*>(T2->awy[hp]);
+                    float tmp[20];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) { const f4 v = src[q]; tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w; }
+#pragma unroll
+                    for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) wy[cp][t] = tmp[cp * 9 + t];
+                }
+                const float cb0 = T2->cbrow[hp][0], cb1 = T2->cbrow[hp][3];
+                f2 acc[4] = {mk2(-cb0, -cb0), mk2(-cb1, -cb1), mk2(-cb0, -cb0), mk2(-cb1, -cb1)};
+#pragma unroll
+                for (int aa = 0; aa < 3; ++aa) {
+                    f2 in[6];
+                    ld6<PW>(XR, (ry + 7 + aa) * PW + 2 * (g + 3), in);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int bb = 0; bb < 3; ++bb) acc[j] = fma2s(in[j + bb], wy[j & 1][aa * 3 + bb], acc[j]);
+                }
+                const int gy = ty0 + ry, gx = tx0 + 4 * g;
+                if (gy < 0 || gy >= H || gx < 0 || gx >= W) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] = mk2(0.f, 0.f);
+                }
+                st4<PW>(Y0, (ry + 7) * PW + 2 * (g + 3), acc[0], acc[1], acc[2], acc[3]);
+            }
+        } }
+        R2L_SYNC();
+
+        // ---- B3: Y1 = sharpen(Y0) on rows -6..TH+5, runs -2..G+1 (overwrites the raw window) ----------------------
+        // Pad rows (-2,-1,H,H+1) evaluate the stencil at the mirrored row; runs outside the image are not stored,
+        // their pad columns are written by the first / last run inside the image.
+        { R2L_FOR_THREADS(NT) {
+            float ws[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) ws[t] = T->Ws[t];
+            for (int item = tid; item < Cfg::Y1H * (G + 4); item += NT) {
+                const int rr = item / (G + 4), g = item - rr * (G + 4) - 2;
+                const int gy = ty0 - 6 + rr, gx = tx0 + 4 * g;
+                if (gx < 0 || gx >= W) continue;
+                int sr = rr;                                           // Y0 rows sr .. sr+2 <-> image rows gy-1 .. gy+1
+                if ((gy < 0 && gy >= -2) || (gy >= H && gy <= H + 1)) sr = mirror(gy, H) - (ty0 - 6);
+                f2 acc[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
+#pragma unroll
+                for (int aa = 0; aa < 3; ++aa) {
+                    f2 in[6];
+                    ld6<PW>(Y0, (sr + aa) * PW + 2 * (g + 3), in);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int bb = 0; bb < 3; ++bb) acc[j] = fma2s(in[j + bb], ws[aa * 3 + bb], acc[j]);
+                }
+                st4<PW>(Y1, rr * PW + 2 * (g + 3), acc[0], acc[1], acc[2], acc[3]);
+                if (gx == 0) { site3<PW>(Y1, rr, 4 * (g + 3) - 1) = acc[1]; site3<PW>(Y1, rr, 4 * (g + 3) - 2) = acc[2]; }
+                if (gx + 4 == W) { site3<PW>(Y1, rr, 4 * (g + 3) + 4) = acc[2]; site3<PW>(Y1, rr, 4 * (g + 3) + 5) = acc[1]; }
+            }
+        } }
+        R2L_SYNC();
+
+        // ---- B4: forward tail recomputed on the F region; grad_out pulled back to (gY2, gU, gV); gamma statistic ----
+        { R2L_FOR_THREADS(NT) {
+            float wg[25], m2[9];
+#pragma unroll
+            for (int t = 0; t < 25; ++t) wg[t] = T->Wg[t];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) m2[t] = T->M2[t];
+            const float invg = T->invg;
+            Bwd3Acc& acc = R2L_ACC(accs, tid);
+            for (int item = tid; item < Cfg::FH * GG; item += NT) {
+                const int rr = item / GG, g = item - rr * GG - 1;
+                const int r = rr - 4;
+                const int gy = ty0 + r, gx = tx0 + 4 * g;
+                f2 y2[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
+#pragma unroll
+                for (int aa = 0; aa < 5; ++aa) {
+                    f2 in[8];
+                    ld8<PW>(Y1, (r + aa + 4) * PW + 2 * (g + 3), in);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int bb = 0; bb < 5; ++bb) y2[j] = fma2s(in[j + bb], wg[aa * 5 + bb], y2[j]);
+                }
+                f2 u[4], v[4];
+                ld4<PN>(PU, (r + 4) * PN + 2 * (g + 2), u);
+                ld4<PN>(PV, (r + 4) * PN + 2 * (g + 2), v);
+                const bool valid = gy >= 0 && gy < H && gx >= 0 && gx < W;
+                const bool owned = r >= 0 && r < TH && g >= 0 && g < G;
+                const size_t pix = valid ? (size_t)gy * W + gx : 0;
+                f2 gy2[4], gu[4], gv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { gy2[j] = mk2(0.f, 0.f); gu[j] = mk2(0.f, 0.f); gv[j] = mk2(0.f, 0.f); }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float ga[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
+                        const f4 xa = *reinterpret_cast<const f4*>(a.gout + ((size_t)b0 * 3 + k) * plane + pix);
+                        ga[0] = xa.x; ga[1] = xa.y; ga[2] = xa.z; ga[3] = xa.w;
+                        if (!dup) {
+                            const f4 xb = *reinterpret_cast<const f4*>(a.gout + ((size_t)b1 * 3 + k) * plane + pix);
+                            gb[0] = xb.x; gb[1] = xb.y; gb[2] = xb.z; gb[3] = xb.w;
+                        }
+                    }
+                    float ad[4] = {0.f, 0.f, 0.f, 0.f};
+                    float t_gs = 0.f, t_c1 = 0.f, t_c2 = 0.f, t_sc = 0.f, t_sh = 0.f;
+                    if (Cfg::TAIL) {
+                        t_gs = a.gtail[k]; t_c1 = a.gtail[3 + k]; t_c2 = a.gtail[6 + k]; t_sc = a.gtail[9 + k]; t_sh = a.gtail[12 + k];
+                        if (a.additive && valid) {
+                            const f4 x = *reinterpret_cast<const f4*>(a.additive + (size_t)k * plane + pix);
+                            ad[0] = x.x; ad[1] = x.y; ad[2] = x.z; ad[3] = x.w;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const f2 rgb = fma2s(v[j], m2[k * 3 + 2], fma2s(u[j], m2[k * 3 + 1], mul2s(y2[j], m2[k * 3])));
+                        const f2 cl = mk2(fminf(fmaxf(rgb.x, kClipLo), kClipHi), fminf(fmaxf(rgb.y, kClipLo), kClipHi));
+                        const f2 l2 = mk2(fast_log2(cl.x), fast_log2(cl.y));
+                        const f2 o = mk2(fast_exp2(invg * l2.x), fast_exp2(invg * l2.y));
+                        f2 Gv = mk2(ga[j], gb[j]);
+                        if (Cfg::TAIL) {
+                            const float ya = fmaf_(o.x + ad[j], t_sc, t_sh), yb = fmaf_(o.y + ad[j], t_sc, t_sh);
+                            Gv = mk2(t_gs * (Gv.x - t_c1 - t_c2 * ya), t_gs * (Gv.y - t_c1 - t_c2 * yb));
+                            if (!valid) Gv = mk2(0.f, 0.f);
+                            if (dup) Gv.y = 0.f;
+                        }
+                        const f2 go = mul2vv(Gv, o);
+                        if (owned) acc.sg = fma2vv(go, l2, acc.sg);
+                        // clamp backward mask (inclusive at both ends): the value passed iff clamping left it unchanged
+                        const f2 gr = mk2(rgb.x == cl.x ? go.x * invg * fast_rcp(cl.x) : 0.f,
+                                          rgb.y == cl.y ? go.y * invg * fast_rcp(cl.y) : 0.f);
+                        gy2[j] = fma2s(gr, m2[k * 3 + 0], gy2[j]);
+                        gu[j] = fma2s(gr, m2[k * 3 + 1], gu[j]);
+                        gv[j] = fma2s(gr, m2[k * 3 + 2], gv[j]);
+                    }
+                }
+                st4<PN>(PG, (r + 4) * PN + 2 * (g + 2), gy2[0], gy2[1], gy2[2], gy2[3]);
+                st4<PN>(PU, (r + 4) * PN + 2 * (g + 2), gu[0], gu[1], gu[2], gu[3]);
+                st4<PN>(PV, (r + 4) * PN + 2 * (g + 2), gv[0], gv[1], gv[2], gv[3]);
+            }
+        } }
+        R2L_SYNC();
+
+        // ---- B5: gY1 on the padded domain = corr^T(gY2, Wg), rows -2..TH+1, runs -1..G; flipped Wg statistic --------
+        { R2L_FOR_THREADS(NT) {
+            float wg[25];
+#pragma unroll
+            for (int t = 0; t < 25; ++t) wg[t] = T->Wg[t];
+            Bwd3Acc& acc = R2L_ACC(accs, tid);
+            // statistic domain: owned rectangle, extended over the pad ring on image-border sides (products vanish
+            // beyond the ring because gY2 is zero outside the image)
+            const int sr0 = e_top ? -2 : 0, sr1 = e_bot ? TH + 2 : TH, sg0 = e_lft ? -1 : 0, sg1 = e_rgt ? G + 1 : G;
+            for (int item = tid; item < Cfg::G1H * GG; item += NT) {
+                const int rr = item / GG, g = item - rr * GG - 1;
+                const int r = rr - 2;
+                const bool stat = r >= sr0 && r < sr1 && g >= sg0 && g < sg1;
+                f2 c[4];
+                ld4<PW>(Y1, (r + 6) * PW + 2 * (g + 3), c);
+                f2 out[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    f2 row[8];                                          // gY2 row q.y - 2 + d, columns q.x - 2 .. q.x + 5
+                    ld8<PN>(PG, (r + 2 + d) * PN + 2 * (g + 2), row);
+                    const int aa = 4 - d;                               // tap row whose transpose reaches this row
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int bb = 0; bb < 5; ++bb) out[j] = fma2s(row[j + 4 - bb], wg[aa * 5 + bb], out[j]);
+                    if (stat) {
+#pragma unroll
+                        for (int bb = 0; bb < 5; ++bb) {
+                            f2 t = mul2vv(c[0], row[4 - bb]);
+#pragma unroll
+                            for (int j = 1; j < 4; ++j) t = fma2vv(c[j], row[j + 4 - bb], t);
+                            acc.wg[aa * 5 + bb] += t.x + t.y;
+                        }
+                    }
+                }
+                st4<PN>(GY1, rr * PN + 2 * (g + 2), out[0], out[1], out[2], out[3]);
+            }
+        } }
+        R2L_SYNC();
+        if (border) {
+            // fold of the reflect-2 padding: every in-image site within 2 of the border gathers its pad pre-images
+            // (which only it owns) and clears them, so gY1 is exact zero outside the image afterwards
+            { R2L_FOR_THREADS(NT) {
+                const int ry0 = ty0 - 2, ry1 = ty0 + TH + 2, rx0 = tx0 - 4, rx1 = tx0 + TW + 4;     // region of GY1
+                const int ya = imax(ry0, 0), yb = imin(ry1, H), xa = imax(rx0, 0), xb = imin(rx1, W);
+                const int nrow = yb - ya, ncol = xb - xa;
+                const int cand_y[4] = {1, 2, H - 3, H - 2}, cand_x[4] = {1, 2, W - 3, W - 2};
+                for (int i = tid; i < 4 * (ncol + nrow); i += NT) {
+                    int ty, tx;
+                    if (i < 4 * ncol) {                                 // target rows x all columns
+                        const int c = i / ncol;
+                        ty = cand_y[c]; tx = xa + (i - c * ncol);
+                        bool again = false;
+                        for (int c2 = 0; c2 < c; ++c2) again |= cand_y[c2] == ty;
+                        if (again || ty < ya || ty >= yb) continue;
+                    } else {                                            // target columns x the other rows
+                        const int i2 = i - 4 * ncol, c = i2 / nrow;
+                        tx = cand_x[c]; ty = ya + (i2 - c * nrow);
+                        bool again = false;
+                        for (int c2 = 0; c2 < c; ++c2) again |= cand_x[c2] == tx;
+                        if (again || tx < xa || tx >= xb) continue;
+                        int tmp[3];
+                        if (preimages2(ty, H, tmp) > 1) continue;      // a target row: handled above
+                    }
+                    int ys[3], xs[3];
+                    const int ny = preimages2(ty, H, ys), nx = preimages2(tx, W, xs);
+                    if (ny * nx == 1) continue;
+                    f2 s = mk2(0.f, 0.f);
+                    for (int iy = 0; iy < ny; ++iy)
+                        for (int ix = 0; ix < nx; ++ix) {
+                            const int py = ys[iy], px = xs[ix];
+                            if (py < ry0 || py >= ry1 || px < rx0 || px >= rx1) continue;
+                            f2& ref = site3<PN>(GY1, py - ry0, px - (tx0 - 8));
+                            s = add2v(s, ref);
+                            if (iy | ix) ref = mk2(0.f, 0.f);
+                        }
+                    site3<PN>(GY1, ty - ry0, tx - (tx0 - 8)) = s;
+                }
+            } }
+            R2L_SYNC();
+        }
+
+        // ---- B6: gY0 = corr^T(gY1, Ws) (zero pad) on rows -1..TH, runs -1..G, zero outside the image; Ws statistic ----
+        { R2L_FOR_THREADS(NT) {
+            float ws[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) ws[t] = T->Ws[t];
+            Bwd3Acc& acc = R2L_ACC(accs, tid);
+            for (int item = tid; item < (TH + 2) * GG; item += NT) {
+                const int rr = item / GG, g = item - rr * GG - 1;
+                const int r = rr - 1;
+                const int qy = ty0 + r, qx = tx0 + 4 * g;
+                const bool owned = r >= 0 && r < TH && g >= 0 && g < G;
+                f2 c[4];
+                ld4<PW>(Y0, (r + 7) * PW + 2 * (g + 3), c);
+                f2 out[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    f2 row[6];                                          // gY1 row q.y - 1 + d, columns q.x - 1 .. q.x + 4
+                    ld6<PN>(GY1, (r + 1 + d) * PN + 2 * (g + 2), row);
+                    const int aa = 2 - d;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int bb = 0; bb < 3; ++bb) out[j] = fma2s(row[j + 2 - bb], ws[aa * 3 + bb], out[j]);
+                    if (owned) {
+#pragma unroll
+                        for (int bb = 0; bb < 3; ++bb) {
+                            f2 t = mul2vv(c[0], row[2 - bb]);
+#pragma unroll
+                            for (int j = 1; j < 4; ++j) t = fma2vv(c[j], row[j + 2 - bb], t);
+                            acc.ws[aa * 3 + bb] += t.x + t.y;
+                        }
+                    }
+                }
+                if (qy < 0 || qy >= H || qx < 0 || qx >= W) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) out[j] = mk2(0.f, 0.f);
+                }
+                st4<PN>(PG, (r + 4) * PN + 2 * (g + 2), out[0], out[1], out[2], out[3]);
+            }
+        } }
+        R2L_SYNC();
+
+        // ---- B7: Q' / P statistics and the padded g_raw from the (gY0, gU, gV) windows ----------------------------------
+        // domain: owned rectangle, plus the reflect-1 pad ring where the tile ends exactly at the image border
+        { R2L_FOR_THREADS(NT) {
+            const int rp = (tid >> 5) & 1, slot = ((tid >> 6) << 5) | (tid & 31);
+            Bwd3Acc& acc = R2L_ACC(accs, tid);
+            float awq[2][3][9];
+            if (Cfg::GRAW) {
+#pragma unroll
+                for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) awq[cp][k][t] = T->AWq[2 * rp + cp][k][t];
+            }
+            const int r_lo = e_top ? -1 : 0, r_hi = imin(TH + ((ty0 + TH == H) ? 1 : 0), H + 1 - ty0);
+            const int g_lo = e_lft ? -1 : 0, g_hi = G + ((tx0 + TW == W) ? 1 : 0);
+            const int r_first = r_lo + ((r_lo ^ rp) & 1);
+            const int nruns = g_hi - g_lo, nrows = r_hi > r_first ? (r_hi - r_first + 1) >> 1 : 0;
+            for (int i = slot; i < nrows * nruns; i += HALF) {
+                const int ri = nruns == G ? i / G : i / nruns;
+                const int g = g_lo + i - ri * nruns;
+                const int r = r_first + 2 * ri;
+                const int qy = ty0 + r, qx = tx0 + 4 * g;
+                // raw centres of the 4 sites (the reflected mosaic on pad sites)
+                f2 c[4];
+                if (TMA && sizeof(RawT) == 4 && qy >= 0 && qy < H && qx >= 0 && qx < W) {
+                    const f4 xa = *reinterpret_cast<const f4*>(reinterpret_cast<const float*>(imgA) + (size_t)qy * W + qx);
+                    const f4 xb = *reinterpret_cast<const f4*>(reinterpret_cast<const float*>(imgB) + (size_t)qy * W + qx);
+                    c[0] = mk2(xa.x, xb.x); c[1] = mk2(xa.y, xb.y); c[2] = mk2(xa.z, xb.z); c[3] = mk2(xa.w, xb.w);
+                } else {
+                    const int sy = mirror_clamped(qy, H);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int sx = mirror_clamped(qx + j, W);
+                        c[j] = mk2(RawLoad<RawT>::get(imgA + (size_t)sy * W + sx, a.denom),
+                                   RawLoad<RawT>::get(imgB + (size_t)sy * W + sx, a.denom));
+                    }
+                }
+                f2 graw[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    f2* pl = k == 0 ? PG : (k == 1 ? PU : PV);
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        f2 row[6];                                      // g_yuv[k] row q.y - 1 + d
+                        ld6<PN>(pl, (r + 3 + d) * PN + 2 * (g + 2), row);
+                        const int aa = 2 - d;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int bb = 0; bb < 3; ++bb) {
+                                const f2 t = row[j + 2 - bb];                                   // g_yuv[k](q - (a-1, b-1))
+                                acc.q[j & 1][k][aa * 3 + bb] = fmaf_(c[j].x, t.x, fmaf_(c[j].y, t.y, acc.q[j & 1][k][aa * 3 + bb]));
+                                if (Cfg::GRAW) graw[j] = fma2s(t, awq[j & 1][k][aa * 3 + bb], graw[j]);
+                            }
+                        if (d == 1) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc.p[j & 1][k] += row[j + 1].x + row[j + 1].y;
+                        }
+                    }
+                }
+                if (Cfg::GRAW) st4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), graw[0], graw[1], graw[2], graw[3]);
+            }
+        } }
+        R2L_SYNC();
+        if (Cfg::GRAW) {
+            // owned sites -> global, folding the reflect-1 pad ring onto rows/columns 1 and n-2 on the way
+            { R2L_FOR_THREADS(NT) {
+                for (int item = tid; item < TH * G; item += NT) {
+                    const int r = item / G, g = item - r * G;
+                    const int qy = ty0 + r, qx = tx0 + 4 * g;
+                    if (qy >= H || qx >= W) continue;
+                    f2 v[4];
+                    ld4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), v);
+                    if (border && (qy == 1 || qy == H - 2 || qx == 0 || qx + 4 == W)) {
+                        for (int j = 0; j < 4; ++j) {
+                            int ys[3], xs[3];
+                            const int ny = preimages1(qy, H, ys), nx = preimages1(qx + j, W, xs);
+                            if (ny * nx == 1) continue;
+                            f2 s = mk2(0.f, 0.f);
+                            for (int iy = 0; iy < ny; ++iy)
+                                for (int ix = 0; ix < nx; ++ix)
+                                    s = add2v(s, site3<PN>(GY1, ys[iy] - (ty0 - 2), xs[ix] - (tx0 - 8)));
+                            v[j] = s;
+                        }
+                    }
+                    float* pa = a.graw + (size_t)b0 * plane + (size_t)qy * W + qx;
+                    f4 va; va.x = v[0].x; va.y = v[1].x; va.z = v[2].x; va.w = v[3].x;
+                    *reinterpret_cast<f4*>(pa) = va;
+                    if (!dup) {
+                        float* pb = a.graw + (size_t)b1 * plane + (size_t)qy * W + qx;
+                        f4 vb; vb.x = v[0].y; vb.y = v[1].y; vb.z = v[2].y; vb.w = v[3].y;
+                        *reinterpret_cast<f4*>(pb) = vb;
+                    }
+                }
+            } }
+            // no barrier: the planes this pass reads (GY1) are next written by the following tile's B5
+        }
+    }
+
+    // ---- CTA reduction of the per-thread statistics into the kStat* layout (deterministic, fixed order) -------------
+    float* part = a.partials + (size_t)cta * kStatPitch;
+    constexpr int RP = kBwd3AccFloats + 1;                           // odd pitch: conflict-free column reads
+    float* red = reinterpret_cast<float*>(XR);
+    { R2L_FOR_THREADS(NT) {
+        const float* src = reinterpret_cast<const float*>(&R2L_ACC(accs, tid));
+        for (int i = 0; i < kBwd3AccFloats; ++i) red[tid * RP + i] = src[i];
+    } }
+    R2L_SYNC();
+    { R2L_FOR_THREADS(NT) {
+        for (int s = tid; s < kNumStats; s += NT) {
+            float sum = 0.f;
+            if (s == kStatGamma) {
+                for (int t = 0; t < NT; ++t) sum += red[t * RP] + red[t * RP + 1];
+            } else if (s < kStatQ) {                                 // Wg, Ws: same slot in every thread
+                for (int t = 0; t < NT; ++t) sum += red[t * RP + s + 1];
+            } else {
+                int k, parp, tt = 0;
+                bool is_q;
+                if (s < kStatP) { const int rI = s - kStatQ; k = rI / 36; parp = (rI - 36 * k) / 9; tt = rI - 36 * k - 9 * parp; is_q = true; }
+                else { const int rI = s - kStatP; k = rI / 4; parp = rI - 4 * k; is_q = false; }
+                // Q[k][par(p)][t] = Q'[par(q) = par_tap(par(p), t)][k][t];  P is already p-indexed (p = q)
+                const int parq = is_q ? par_tap(parp, tt) : parp;
+                const int rpq = parq >> 1, cpq = parq & 1;
+                const int off = is_q ? 36 + (cpq * 3 + k) * 9 + tt : 36 + 54 + cpq * 3 + k;
+                for (int t = 0; t < NT; ++t)
+                    if (((t >> 5) & 1) == rpq) sum += red[t * RP + off];
+            }
+            part[s] = sum;
+        }
+    } }
+}
+
+}  // namespace r2l

@@ -1,0 +1,7 @@
+// third-generation backward kernels, uint16 raw
+#include "isp_bwd_tu.cuh"
+namespace r2l {
+int launch_backward3_u16(const BwdArgs& a, cudaStream_t st, int* grid_used) {
+    return launch_backward3_impl<uint16_t>(a, st, grid_used);
+}
+}  // namespace r2l

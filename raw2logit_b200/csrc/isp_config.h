@@ -3,6 +3,7 @@
 #include "isp_core.cuh"
 #include "isp_fwd2.cuh"
 #include "isp_bwd2.cuh"
+#include "isp_bwd3.cuh"
 
 namespace r2l {
 using FwdDefault = FwdCfg<32, 64, 256>;          // v1 (scalar) -- kept for the emulation cross-check only
@@ -11,5 +12,7 @@ using BwdNoRaw = BwdCfg<32, 64, 256, false>;     // v1 (scalar) -- emulation cro
 using Bwd2NoRaw = Bwd2Cfg<32, 64, 256, false>;
 using Bwd2WithRaw = Bwd2Cfg<32, 64, 256, true>;
 using BwdWithRaw = BwdCfg<32, 64, 256, true>;
+// v3: branch-free padded-domain phases; <TH, TW, NT, GRAW, TAIL>
+template <bool GRAW, bool TAIL> using Bwd3 = Bwd3Cfg<32, 64, 256, GRAW, TAIL>;
 constexpr int kMaxCtas = 2048;          // upper bound on persistent CTAs == rows of the statistics workspace
 }  // namespace r2l

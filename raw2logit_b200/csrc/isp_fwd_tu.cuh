@@ -1,0 +1,45 @@
+// isp_fwd_tu.cuh -- forward kernels + launcher for one raw element type (included by isp_fwd_f32.cu / isp_fwd_u16.cu)
+#pragma once
+#include "isp_launch.h"
+
+namespace r2l {
+
+template <class Cfg, typename RawT, bool STATS>
+__global__ void __launch_bounds__(Cfg::NT, 2) isp_forward_kernel(FwdArgs a, TileGrid grid) {
+    extern __shared__ __align__(128) float smem[];
+    fwd2_cta<Cfg, RawT, STATS, false>(blockIdx.x, gridDim.x, a, grid, smem);
+}
+// same kernel, raw window delivered by TMA (tensor map over raw as (W, H, B))
+template <class Cfg, typename RawT, bool STATS>
+__global__ void __launch_bounds__(Cfg::NT, 2) isp_forward_tma_kernel(FwdArgs a, TileGrid grid,
+                                                                     const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float smem[];
+    fwd2_cta<Cfg, RawT, STATS, true>(blockIdx.x, gridDim.x, a, grid, smem, &tmap);
+}
+
+template <class Cfg, typename RawT, bool STATS>
+static int launch_forward_t(const FwdArgs& a, cudaStream_t st, int* grid_used) {
+    const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);     // tiles of image pairs
+    int g = 0;
+    CUtensorMap tmap;
+    if (make_raw_tensor_map(&tmap, a.raw, (int)sizeof(RawT), a.B, a.H, a.W, Cfg::P, Cfg::RH)) {
+        int rc = persistent_grid(isp_forward_tma_kernel<Cfg, RawT, STATS>, Cfg::NT, Cfg::kSmemBytesTma, grid.n, &g);
+        if (rc != R2L_OK) return rc;
+        isp_forward_tma_kernel<Cfg, RawT, STATS><<<g, Cfg::NT, Cfg::kSmemBytesTma, st>>>(a, grid, tmap);
+    } else {
+        int rc = persistent_grid(isp_forward_kernel<Cfg, RawT, STATS>, Cfg::NT, Cfg::kSmemBytes, grid.n, &g);
+        if (rc != R2L_OK) return rc;
+        isp_forward_kernel<Cfg, RawT, STATS><<<g, Cfg::NT, Cfg::kSmemBytes, st>>>(a, grid);
+    }
+    if (grid_used) *grid_used = g;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? R2L_OK : cuda_fail(e);
+}
+
+template <typename RawT>
+static int launch_forward_impl(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used) {
+    return stats ? launch_forward_t<Fwd2Default, RawT, true>(a, st, grid_used)
+                 : launch_forward_t<Fwd2Default, RawT, false>(a, st, grid_used);
+}
+
+}  // namespace r2l

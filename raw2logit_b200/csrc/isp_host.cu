@@ -1,34 +1,17 @@
-// isp_kernels.cu -- sm_100a kernels and the C ABI (include/r2l_isp.h) of the fused differentiable ISP.
+// isp_host.cu -- the C ABI (include/r2l_isp.h) of the fused differentiable ISP, its argument checks and dispatch,
+// and the small auxiliary kernels (BatchNorm tail, statistics finish, CFA split).  The fused forward / backward
+// kernels live in their own translation units (isp_fwd_*.cu, isp_bwd_*.cu, isp_generic.cu; see isp_launch.h).
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC  (see _build.py)
 // No torch headers, no host-side state: every call validates its arguments, enqueues kernels on the caller's
 // stream and returns.
-#include <cuda.h>            // CUtensorMap types only; the encoder is fetched through the runtime (no libcuda link)
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include <stdlib.h>
-
-#include "../../include/r2l_isp.h"
-#include "isp_config.h"
+#include "isp_launch.h"
 
 namespace r2l {
 
 // ---------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------
-template <class Cfg, typename RawT, bool STATS>
-__global__ void __launch_bounds__(Cfg::NT, 2) isp_forward_kernel(FwdArgs a, TileGrid grid) {
-    extern __shared__ __align__(128) float smem[];
-    fwd2_cta<Cfg, RawT, STATS, false>(blockIdx.x, gridDim.x, a, grid, smem);
-}
-// same kernel, raw window delivered by TMA (tensor map over raw as (W, H, B))
-template <class Cfg, typename RawT, bool STATS>
-__global__ void __launch_bounds__(Cfg::NT, 2) isp_forward_tma_kernel(FwdArgs a, TileGrid grid,
-                                                                     const __grid_constant__ CUtensorMap tmap) {
-    extern __shared__ __align__(128) float smem[];
-    fwd2_cta<Cfg, RawT, STATS, true>(blockIdx.x, gridDim.x, a, grid, smem, &tmap);
-}
-
 // ---- train-mode BatchNorm2d(3, affine=False) tail (pipeline_torch.py:168, 216-217) -------------------------
 // per-CTA channel sums -> batch mean / biased variance -> {scale, shift}; running statistics updated in place
 // exactly like torch (momentum update, unbiased variance for the running estimate).
@@ -112,18 +95,6 @@ __global__ void bn_backward_finish_kernel(const float* partials, const float* af
     gtail[6 + c] = (float)(s2 / count);         // c2  = mean(gy * yhat)
     gtail[9 + c] = affine[c];                   // ysc
     gtail[12 + c] = affine[3 + c];              // ysh
-}
-
-template <class Cfg, typename RawT>
-__global__ void __launch_bounds__(Cfg::NT, 1) isp_backward_kernel(BwdArgs a, TileGrid grid) {
-    extern __shared__ __align__(128) float smem[];
-    bwd2_cta<Cfg, RawT, false>(blockIdx.x, gridDim.x, a, grid, smem);
-}
-template <class Cfg, typename RawT>
-__global__ void __launch_bounds__(Cfg::NT, 1) isp_backward_tma_kernel(BwdArgs a, TileGrid grid,
-                                                                      const __grid_constant__ CUtensorMap tmap) {
-    extern __shared__ __align__(128) float smem[];
-    bwd2_cta<Cfg, RawT, true>(blockIdx.x, gridDim.x, a, grid, smem, &tmap);
 }
 
 // statistics of all CTAs -> 132 parameter gradients.  One CTA; sums over CTAs in double, in a fixed order.
@@ -211,7 +182,7 @@ __global__ void mosaic_backward_kernel(const float* gout, int B, int H, int W, i
 // ---------------------------------------------------------------------------------------------------------
 static thread_local int g_last_cuda_error = 0;
 
-static int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return R2L_ERR_CUDA; }
+int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return R2L_ERR_CUDA; }
 
 static Params to_params(const r2l_isp_params* p) {
     Params q;
@@ -224,7 +195,6 @@ static bool params_ok(const r2l_isp_params* p) {
     return p && p->black_level && p->white_balance && p->colour_correction && p->gamma_correct &&
            p->debayer_weight && p->sharpen_weight && p->gauss_weight && p->rgb2yuv && p->yuv2rgb;
 }
-static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 static int check_common(const void* raw, int raw_dtype, int B, int H, int W, const r2l_isp_params* params) {
     if (raw_dtype != R2L_F32 && raw_dtype != R2L_U16) return R2L_ERR_BAD_DTYPE;
@@ -232,26 +202,6 @@ static int check_common(const void* raw, int raw_dtype, int B, int H, int W, con
     if (B > 0 && !raw) return R2L_ERR_NULL_POINTER;
     if (!params_ok(params)) return R2L_ERR_NULL_POINTER;
     if (!aligned(raw, raw_dtype == R2L_F32 ? 4 : 2)) return R2L_ERR_MISALIGNED;
-    return R2L_OK;
-}
-
-// persistent grid: one wave of resident CTAs (or fewer when the job is small)
-template <typename K>
-static int persistent_grid(K kernel, int threads, size_t smem, int n_tiles, int* grid_out) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return cuda_fail(e);
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return cuda_fail(e);
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
-    if (e != cudaSuccess) return cuda_fail(e);
-    if (per_sm < 1) return R2L_ERR_BAD_ARGUMENT;
-    int g = sms * per_sm;
-    if (g > n_tiles) g = n_tiles;
-    if (g > kMaxCtas) g = kMaxCtas;
-    *grid_out = g;
     return R2L_OK;
 }
 
@@ -270,8 +220,8 @@ static EncodeTiledFn encode_tiled_fn() {
     }();
     return fn;
 }
-// false when the shape/pointer does not meet TMA's 16-byte rules (then the generic loader runs)
-static bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_bytes, int B, int H, int W, int box_w,
+// false when the shape/pointer does not meet TMA's 16-byte rules (then a non-TMA kernel runs)
+bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_bytes, int B, int H, int W, int box_w,
                                 int box_h) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
@@ -289,44 +239,27 @@ static bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_byte
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <class Cfg, typename RawT, bool STATS>
-static int launch_forward(const FwdArgs& a, cudaStream_t st, int* grid_used = nullptr) {
-    const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);     // tiles of image pairs
-    int g = 0;
-    CUtensorMap tmap;
-    if (make_raw_tensor_map(&tmap, a.raw, (int)sizeof(RawT), a.B, a.H, a.W, Cfg::P, Cfg::RH)) {
-        int rc = persistent_grid(isp_forward_tma_kernel<Cfg, RawT, STATS>, Cfg::NT, Cfg::kSmemBytesTma, grid.n, &g);
-        if (rc != R2L_OK) return rc;
-        isp_forward_tma_kernel<Cfg, RawT, STATS><<<g, Cfg::NT, Cfg::kSmemBytesTma, st>>>(a, grid, tmap);
-    } else {
-        int rc = persistent_grid(isp_forward_kernel<Cfg, RawT, STATS>, Cfg::NT, Cfg::kSmemBytes, grid.n, &g);
-        if (rc != R2L_OK) return rc;
-        isp_forward_kernel<Cfg, RawT, STATS><<<g, Cfg::NT, Cfg::kSmemBytes, st>>>(a, grid);
-    }
-    if (grid_used) *grid_used = g;
+// statistics of the backward CTAs -> 132 gradients
+static int launch_finish(const BwdArgs& a, int n_cta, float* grads, cudaStream_t st) {
+    isp_backward_finish_kernel<<<1, kFinishThreads, 0, st>>>(a.P, a.partials, n_cta, grads);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);
 }
 
-template <class Cfg, typename RawT>
-static int launch_backward(const BwdArgs& a, float* grads, cudaStream_t st) {
-    const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);     // tiles of image pairs
+static int launch_forward_any(const FwdArgs& a, int raw_dtype, bool stats, cudaStream_t st, int* grid_used) {
+    return raw_dtype == R2L_F32 ? launch_forward_f32(a, stats, st, grid_used) : launch_forward_u16(a, stats, st, grid_used);
+}
+
+// vectorised third-generation kernel when the shape / alignment allows, generic scalar kernel otherwise
+static int launch_backward_any(const BwdArgs& a, int raw_dtype, float* grads, cudaStream_t st) {
     int g = 0;
-    CUtensorMap tmap;
-    if (make_raw_tensor_map(&tmap, a.raw, (int)sizeof(RawT), a.B, a.H, a.W, Cfg::PW, Cfg::RH)) {
-        int rc = persistent_grid(isp_backward_tma_kernel<Cfg, RawT>, Cfg::NT, Cfg::kSmemBytesTma, grid.n, &g);
-        if (rc != R2L_OK) return rc;
-        isp_backward_tma_kernel<Cfg, RawT><<<g, Cfg::NT, Cfg::kSmemBytesTma, st>>>(a, grid, tmap);
-    } else {
-        int rc = persistent_grid(isp_backward_kernel<Cfg, RawT>, Cfg::NT, Cfg::kSmemBytes, grid.n, &g);
-        if (rc != R2L_OK) return rc;
-        isp_backward_kernel<Cfg, RawT><<<g, Cfg::NT, Cfg::kSmemBytes, st>>>(a, grid);
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e);
-    isp_backward_finish_kernel<<<1, kFinishThreads, 0, st>>>(a.P, a.partials, g, grads);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? R2L_OK : cuda_fail(e);
+    int rc = kNotServed;
+    const char* force = getenv("R2L_ISP_FORCE_GENERIC");        // debugging knob
+    if (!(force && force[0] == '1'))
+        rc = raw_dtype == R2L_F32 ? launch_backward3_f32(a, st, &g) : launch_backward3_u16(a, st, &g);
+    if (rc == kNotServed) rc = launch_backward_generic(a, raw_dtype, st, &g);
+    if (rc != R2L_OK) return rc;
+    return launch_finish(a, g, grads, st);
 }
 
 }  // namespace r2l
@@ -366,8 +299,7 @@ int r2l_isp_forward(const void* raw, int raw_dtype, float raw_denominator, int B
     a.affine = tail ? tail->affine : nullptr;
     a.out = out; a.chan_partials = nullptr;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return raw_dtype == R2L_F32 ? launch_forward<Fwd2Default, float, false>(a, st)
-                                : launch_forward<Fwd2Default, uint16_t, false>(a, st);
+    return launch_forward_any(a, raw_dtype, false, st, nullptr);
 }
 
 size_t r2l_isp_workspace_bytes(int B, int H, int W) {
@@ -390,8 +322,7 @@ int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominat
     a.additive = additive; a.affine = nullptr; a.out = out; a.chan_partials = static_cast<float*>(workspace);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int g = 0;
-    rc = raw_dtype == R2L_F32 ? launch_forward<Fwd2Default, float, true>(a, st, &g)
-                              : launch_forward<Fwd2Default, uint16_t, true>(a, st, &g);
+    rc = launch_forward_any(a, raw_dtype, true, st, &g);
     if (rc != R2L_OK) return rc;
     bn_finish_kernel<<<1, 32, 0, st>>>(a.chan_partials, g, (double)B * H * W, momentum, eps, running_mean,
                                        running_var, saved_affine);
@@ -437,12 +368,7 @@ int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int 
     BwdArgs a;
     a.raw = raw; a.denom = raw_denominator; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.gout = grad_out; a.gtail = grad_tail; a.additive = additive; a.graw = grad_raw; a.partials = static_cast<float*>(workspace);
-    if (grad_raw) {
-        return raw_dtype == R2L_F32 ? launch_backward<Bwd2WithRaw, float>(a, grad_params, st)
-                                    : launch_backward<Bwd2WithRaw, uint16_t>(a, grad_params, st);
-    }
-    return raw_dtype == R2L_F32 ? launch_backward<Bwd2NoRaw, float>(a, grad_params, st)
-                                : launch_backward<Bwd2NoRaw, uint16_t>(a, grad_params, st);
+    return launch_backward_any(a, raw_dtype, grad_params, st);
 }
 
 int r2l_isp_mosaic(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,

@@ -1,0 +1,51 @@
+// isp_launch.h -- host-side helpers shared by the translation units of libr2l_isp.so (not part of the C ABI).
+#pragma once
+#include <cuda.h>            // CUtensorMap types only; the encoder is fetched through the runtime (no libcuda link)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "../../include/r2l_isp.h"
+#include "isp_config.h"
+
+namespace r2l {
+
+int cuda_fail(cudaError_t e);                      // records the error for r2l_isp_last_cuda_error(), returns R2L_ERR_CUDA
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// persistent grid: one wave of resident CTAs (or fewer when the job is small)
+template <typename K>
+static int persistent_grid(K kernel, int threads, size_t smem, int n_tiles, int* grid_out) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (e != cudaSuccess) return cuda_fail(e);
+    if (per_sm < 1) return R2L_ERR_BAD_ARGUMENT;
+    int g = sms * per_sm;
+    if (g > n_tiles) g = n_tiles;
+    if (g > kMaxCtas) g = kMaxCtas;
+    *grid_out = g;
+    return R2L_OK;
+}
+
+// tensor map over the raw batch: dims (W, H, B), box (box_w, box_h, 2), zero fill outside.
+// false when the shape/pointer does not meet TMA's 16-byte rules (then a non-TMA kernel runs)
+bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_bytes, int B, int H, int W, int box_w, int box_h);
+
+// launchers, one translation unit each (compiled in parallel by _build.py)
+int launch_forward_f32(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used);
+int launch_forward_u16(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used);
+// third-generation backward (TMA-fed); returns kNotServed when the shape / alignment is not served
+int launch_backward3_f32(const BwdArgs& a, cudaStream_t st, int* grid_used);
+int launch_backward3_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
+// generic scalar kernels: any shape, any alignment
+int launch_backward_generic(const BwdArgs& a, int raw_dtype, cudaStream_t st, int* grid_used);
+constexpr int kNotServed = 1;
+
+}  // namespace r2l

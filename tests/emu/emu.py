@@ -12,6 +12,7 @@ LIB = os.path.join(HERE, "libisp_emu.so")
 DEPS = [SRC, os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_core.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_fwd2.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd2.cuh"),
+        os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd3.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_config.h"), os.path.join(ROOT, "include", "r2l_isp.h")]
 
 PARAM_FIELDS = ["black_level", "white_balance", "colour_correction", "gamma_correct", "debayer.weight",
@@ -75,7 +76,7 @@ def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0, vers
 
 
 def backward(raw, state, grad_out, need_raw_grad=True, n_cta=3, denom=65535.0, grad_tail=None, additive=None,
-             version=2):
+             version=3):
     raw = np.ascontiguousarray(raw)
     dtype = 1 if raw.dtype == np.uint16 else 0
     if dtype == 0:

@@ -41,6 +41,21 @@ static void run_backward(const BwdArgs& a, int n_cta, float* grads, int version)
         const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
         std::vector<float> smem(Cfg::kSmemFloats);
         for (int cta = 0; cta < n_cta; ++cta) bwd_cta<Cfg, RawT>(cta, n_cta, a, grid, smem.data());
+    } else if (version == 3) {
+        if (!bwd3_shape_ok(a.H, a.W, Cfg::TH, Cfg::TW)) {           // same dispatch rule as the CUDA launcher
+            run_backward<Cfg, RawT>(a, n_cta, grads, 1);
+            return;
+        }
+        const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);
+        auto go = [&](auto cfg) {
+            using C3 = decltype(cfg);
+            std::vector<float> smem(C3::kSmemBytes / 4 + 4);
+            float* base = smem.data();
+            while (reinterpret_cast<uintptr_t>(base) % 16) ++base;
+            for (int cta = 0; cta < n_cta; ++cta) bwd3_cta<C3, RawT, false>(cta, n_cta, a, grid, base);
+        };
+        if (a.gtail) go(Bwd3Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW, true>());
+        else go(Bwd3Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW, false>());
     } else {
         using C2 = Bwd2Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW>;
         const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, C2::TH, C2::TW);
