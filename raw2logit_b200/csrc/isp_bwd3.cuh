@@ -68,10 +68,12 @@ template <int TH_, int TW_, int NT_, bool GRAW_, bool TAIL_> struct Bwd3Cfg {
     static constexpr size_t kStageBytes = (size_t)2 * RH * PW * 4;
     static constexpr size_t kSmemBytes = kPlaneBytes;
     static constexpr size_t kSmemBytesTma = kStageOffset + kStageBytes + 16;
+    // TMA staging [image][row][pitch]: the box must start on a 16-byte boundary of the global row, so 2-byte raw
+    // starts 16 elements left of the tile (and is 8 wider) where 4-byte raw starts 12 left
+    // (stage x origin = x0 - (elem 2 bytes ? 16 : 12), stage pitch = PW + (elem 2 bytes ? 8 : 0))
     static constexpr int HALF = NT / 2;       // threads per CFA row phase
     static_assert(NT % 64 == 0 && TH % 2 == 0 && TW % 8 == 0, "warp-parity mapping");
     static_assert(Y1H * PW <= kXR, "Y1 aliases the raw window");
-    static_assert((size_t)NT * (kBwd3AccFloats + 1) * 4 <= (size_t)kSites * 8, "reduction scratch");
 };
 
 // shapes the third generation serves (the rest goes to the generic scalar kernel)
@@ -118,14 +120,15 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
     RawT* stage = reinterpret_cast<RawT*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset + Cfg::kStageBytes);
     uint32_t tma_phase = 0;
-    constexpr uint32_t kTmaBytes = 2u * Cfg::RH * PW * sizeof(RawT);
+    constexpr int SX = sizeof(RawT) == 2 ? 16 : 12, SP = sizeof(RawT) == 2 ? PW + 8 : PW;
+    constexpr uint32_t kTmaBytes = 2u * Cfg::RH * SP * sizeof(RawT);
     if (TMA) {
         if (threadIdx.x == 0) {
             mbar_init(mbar, 1);
             if (cta < grid.n) {
                 int pb0, pb1, py0, px0;
                 decode_pair_tile(grid, cta, TH, TW, a.B, pb0, pb1, py0, px0);
-                tma_load_3d(stage, tmap, px0 - 12, py0 - 8, pb0, mbar, kTmaBytes);
+                tma_load_3d(stage, tmap, px0 - SX, py0 - 8, pb0, mbar, kTmaBytes);
             }
         }
         __syncthreads();
@@ -161,8 +164,8 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #ifndef R2L_HOST_EMU
                 if (TMA) {
                     const int sl = imin(imax(sy - (ty0 - 8), 0), Cfg::RH - 1);
-                    const RawT* sa = stage + sl * PW + 4 * lq;
-                    const RawT* sb = sa + Cfg::RH * PW;
+                    const RawT* sa = stage + sl * SP + 4 * lq + (SX - 12);
+                    const RawT* sb = sa + Cfg::RH * SP;
                     if (sizeof(RawT) == 4) {
                         const f4 xa = *reinterpret_cast<const f4*>(sa);
                         const f4 xb = *reinterpret_cast<const f4*>(sb);
@@ -196,7 +199,7 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             if (next < grid.n) {
                 int nb0, nb1, ny0, nx0;
                 decode_pair_tile(grid, next, TH, TW, a.B, nb0, nb1, ny0, nx0);
-                tma_load_3d(stage, tmap, nx0 - 12, ny0 - 8, nb0, mbar, kTmaBytes);
+                tma_load_3d(stage, tmap, nx0 - SX, ny0 - 8, nb0, mbar, kTmaBytes);
             }
         }
 #endif
@@ -636,21 +639,39 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
     }
 
     // ---- CTA reduction of the per-thread statistics into the kStat* layout (deterministic, fixed order) -------------
+    // warps reduce their lanes (all lanes of a warp share the CFA row phase), then one thread per statistic adds the
+    // warp totals in warp order
     float* part = a.partials + (size_t)cta * kStatPitch;
-    constexpr int RP = kBwd3AccFloats + 1;                           // odd pitch: conflict-free column reads
-    float* red = reinterpret_cast<float*>(XR);
-    { R2L_FOR_THREADS(NT) {
-        const float* src = reinterpret_cast<const float*>(&R2L_ACC(accs, tid));
-        for (int i = 0; i < kBwd3AccFloats; ++i) red[tid * RP + i] = src[i];
-    } }
+    constexpr int NW = NT / 32;
+    constexpr int RP = kBwd3AccFloats + 1;
+    float* red = reinterpret_cast<float*>(XR);                       // [NW][RP]
+    R2L_SYNC();                                                      // planes are dead
+#ifdef R2L_HOST_EMU
+    for (int w = 0; w < NW; ++w)
+        for (int i = 0; i < kBwd3AccFloats; ++i) {
+            float sum = 0.f;
+            for (int l = 0; l < 32; ++l) sum += reinterpret_cast<const float*>(&accs[w * 32 + l])[i];
+            red[w * RP + i] = sum;
+        }
+#else
+    {
+        const float* src = reinterpret_cast<const float*>(&accs);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int i = 0; i < kBwd3AccFloats; ++i) {
+            const float v = warp_sum_all(src[i]);
+            if (lane == 0) red[warp * RP + i] = v;
+        }
+    }
+#endif
     R2L_SYNC();
     { R2L_FOR_THREADS(NT) {
         for (int s = tid; s < kNumStats; s += NT) {
             float sum = 0.f;
             if (s == kStatGamma) {
-                for (int t = 0; t < NT; ++t) sum += red[t * RP] + red[t * RP + 1];
+                for (int w = 0; w < NW; ++w) sum += red[w * RP] + red[w * RP + 1];
             } else if (s < kStatQ) {                                 // Wg, Ws: same slot in every thread
-                for (int t = 0; t < NT; ++t) sum += red[t * RP + s + 1];
+                for (int w = 0; w < NW; ++w) sum += red[w * RP + s + 1];
             } else {
                 int k, parp, tt = 0;
                 bool is_q;
@@ -660,8 +681,7 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 const int parq = is_q ? par_tap(parp, tt) : parp;
                 const int rpq = parq >> 1, cpq = parq & 1;
                 const int off = is_q ? 36 + (cpq * 3 + k) * 9 + tt : 36 + 54 + cpq * 3 + k;
-                for (int t = 0; t < NT; ++t)
-                    if (((t >> 5) & 1) == rpq) sum += red[t * RP + off];
+                for (int w = rpq; w < NW; w += 2) sum += red[w * RP + off];      // warps of row phase rpq
             }
             part[s] = sum;
         }
