@@ -42,6 +42,28 @@ R2L_HD f2 mul2vv(f2 a, f2 b) {
 #endif
 }
 
+
+// read-once global data (grad_out): streaming 128-bit load
+R2L_HD f4 ld_stream4(const float* p) {
+#ifdef R2L_HOST_EMU
+    f4 v; v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3]; return v;
+#else
+    return __ldcs(reinterpret_cast<const float4*>(p));
+#endif
+}
+
+// Items of a region = owned rectangle (TH x G runs) first, then its halo ring: HR rows above and below (runs -1..G)
+// and the runs -1 and G beside the owned rows.  The owned items carry the statistics, so putting them first gives
+// every thread the same number of expensive items.
+template <int TH, int G, int HR> R2L_HD void region_item(int i, int& r, int& g) {
+    constexpr int GG = G + 2, TB = HR * GG;
+    if (i < TH * G) { r = i / G; g = i - r * G; return; }
+    int h = i - TH * G;
+    if (h < TB) { const int q = h / GG; r = q - HR; g = h - q * GG - 1; }
+    else if (h < 2 * TB) { h -= TB; const int q = h / GG; r = TH + q; g = h - q * GG - 1; }
+    else { h -= 2 * TB; r = h >> 1; g = (h & 1) ? G : -1; }
+}
+
 struct Bwd3Acc {
     f2 sg;               // sum G o log2(cl), per stream
     float wg[25];        // flipped Gaussian-weight statistic
@@ -333,18 +355,38 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         R2L_SYNC();
 
         // ---- B4: forward tail recomputed on the F region; grad_out pulled back to (gY2, gU, gV); gamma statistic ----
+        // With cl = clip(rgb), l2 = log2(cl), e = cl^(1/g - 1) = 2^((1/g - 1) l2):  o = cl e,  dL/drgb = pass G e / g,
+        // and the gamma statistic sum G o l2 = sum (G e)(cl l2) -- two MUFU per value.
         { R2L_FOR_THREADS(NT) {
-            float wg[25], m2[9];
+            float wg[25], m2[9], m2g[9];
+            const float invg = T->invg, invg1 = T->invg - 1.0f;
 #pragma unroll
             for (int t = 0; t < 25; ++t) wg[t] = T->Wg[t];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) m2[t] = T->M2[t];
-            const float invg = T->invg;
+            for (int t = 0; t < 9; ++t) { m2[t] = T->M2[t]; m2g[t] = m2[t] * invg; }
             Bwd3Acc& acc = R2L_ACC(accs, tid);
             for (int item = tid; item < Cfg::FH * GG; item += NT) {
                 const int rr = item / GG, g = item - rr * GG - 1;
                 const int r = rr - 4;
                 const int gy = ty0 + r, gx = tx0 + 4 * g;
+                const bool valid = gy >= 0 && gy < H && gx >= 0 && gx < W;
+                const bool owned = r >= 0 && r < TH && g >= 0 && g < G;
+                // the grad_out loads have the longest latency of the phase: issue them before the Gaussian
+                f4 ga[3], gb[3], ad[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    ga[k].x = ga[k].y = ga[k].z = ga[k].w = 0.f;
+                    gb[k] = ga[k]; ad[k] = ga[k];
+                }
+                if (valid) {
+                    const size_t pix = (size_t)gy * W + gx;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        ga[k] = ld_stream4(a.gout + ((size_t)b0 * 3 + k) * plane + pix);
+                        if (!dup) gb[k] = ld_stream4(a.gout + ((size_t)b1 * 3 + k) * plane + pix);
+                        if (Cfg::TAIL && a.additive) ad[k] = *reinterpret_cast<const f4*>(a.additive + (size_t)k * plane + pix);
+                    }
+                }
                 f2 y2[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
 #pragma unroll
                 for (int aa = 0; aa < 5; ++aa) {
@@ -358,53 +400,37 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 f2 u[4], v[4];
                 ld4<PN>(PU, (r + 4) * PN + 2 * (g + 2), u);
                 ld4<PN>(PV, (r + 4) * PN + 2 * (g + 2), v);
-                const bool valid = gy >= 0 && gy < H && gx >= 0 && gx < W;
-                const bool owned = r >= 0 && r < TH && g >= 0 && g < G;
-                const size_t pix = valid ? (size_t)gy * W + gx : 0;
                 f2 gy2[4], gu[4], gv[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { gy2[j] = mk2(0.f, 0.f); gu[j] = mk2(0.f, 0.f); gv[j] = mk2(0.f, 0.f); }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    float ga[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
-                        const f4 xa = *reinterpret_cast<const f4*>(a.gout + ((size_t)b0 * 3 + k) * plane + pix);
-                        ga[0] = xa.x; ga[1] = xa.y; ga[2] = xa.z; ga[3] = xa.w;
-                        if (!dup) {
-                            const f4 xb = *reinterpret_cast<const f4*>(a.gout + ((size_t)b1 * 3 + k) * plane + pix);
-                            gb[0] = xb.x; gb[1] = xb.y; gb[2] = xb.z; gb[3] = xb.w;
-                        }
-                    }
-                    float ad[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float gak[4] = {ga[k].x, ga[k].y, ga[k].z, ga[k].w}, gbk[4] = {gb[k].x, gb[k].y, gb[k].z, gb[k].w};
+                    const float adk[4] = {ad[k].x, ad[k].y, ad[k].z, ad[k].w};
                     float t_gs = 0.f, t_c1 = 0.f, t_c2 = 0.f, t_sc = 0.f, t_sh = 0.f;
-                    if (Cfg::TAIL) {
-                        t_gs = a.gtail[k]; t_c1 = a.gtail[3 + k]; t_c2 = a.gtail[6 + k]; t_sc = a.gtail[9 + k]; t_sh = a.gtail[12 + k];
-                        if (a.additive && valid) {
-                            const f4 x = *reinterpret_cast<const f4*>(a.additive + (size_t)k * plane + pix);
-                            ad[0] = x.x; ad[1] = x.y; ad[2] = x.z; ad[3] = x.w;
-                        }
-                    }
+                    if (Cfg::TAIL) { t_gs = a.gtail[k]; t_c1 = a.gtail[3 + k]; t_c2 = a.gtail[6 + k]; t_sc = a.gtail[9 + k]; t_sh = a.gtail[12 + k]; }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const f2 rgb = fma2s(v[j], m2[k * 3 + 2], fma2s(u[j], m2[k * 3 + 1], mul2s(y2[j], m2[k * 3])));
                         const f2 cl = mk2(fminf(fmaxf(rgb.x, kClipLo), kClipHi), fminf(fmaxf(rgb.y, kClipLo), kClipHi));
                         const f2 l2 = mk2(fast_log2(cl.x), fast_log2(cl.y));
-                        const f2 o = mk2(fast_exp2(invg * l2.x), fast_exp2(invg * l2.y));
-                        f2 Gv = mk2(ga[j], gb[j]);
+                        const f2 ex = mul2s(l2, invg1);
+                        const f2 e = mk2(fast_exp2(ex.x), fast_exp2(ex.y));
+                        f2 Gv = mk2(gak[j], gbk[j]);
                         if (Cfg::TAIL) {
-                            const float ya = fmaf_(o.x + ad[j], t_sc, t_sh), yb = fmaf_(o.y + ad[j], t_sc, t_sh);
+                            const f2 o = mul2vv(cl, e);
+                            const float ya = fmaf_(o.x + adk[j], t_sc, t_sh), yb = fmaf_(o.y + adk[j], t_sc, t_sh);
                             Gv = mk2(t_gs * (Gv.x - t_c1 - t_c2 * ya), t_gs * (Gv.y - t_c1 - t_c2 * yb));
                             if (!valid) Gv = mk2(0.f, 0.f);
                             if (dup) Gv.y = 0.f;
                         }
-                        const f2 go = mul2vv(Gv, o);
-                        if (owned) acc.sg = fma2vv(go, l2, acc.sg);
+                        const f2 ge = mul2vv(Gv, e);
+                        if (owned) acc.sg = fma2vv(ge, mul2vv(cl, l2), acc.sg);
                         // clamp backward mask (inclusive at both ends): the value passed iff clamping left it unchanged
-                        const f2 gr = mk2(rgb.x == cl.x ? go.x * invg * fast_rcp(cl.x) : 0.f,
-                                          rgb.y == cl.y ? go.y * invg * fast_rcp(cl.y) : 0.f);
-                        gy2[j] = fma2s(gr, m2[k * 3 + 0], gy2[j]);
-                        gu[j] = fma2s(gr, m2[k * 3 + 1], gu[j]);
-                        gv[j] = fma2s(gr, m2[k * 3 + 2], gv[j]);
+                        const f2 gr = mk2(rgb.x == cl.x ? ge.x : 0.f, rgb.y == cl.y ? ge.y : 0.f);
+                        gy2[j] = fma2s(gr, m2g[k * 3 + 0], gy2[j]);
+                        gu[j] = fma2s(gr, m2g[k * 3 + 1], gu[j]);
+                        gv[j] = fma2s(gr, m2g[k * 3 + 2], gv[j]);
                     }
                 }
                 st4<PN>(PG, (r + 4) * PN + 2 * (g + 2), gy2[0], gy2[1], gy2[2], gy2[3]);
@@ -424,8 +450,9 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             // beyond the ring because gY2 is zero outside the image)
             const int sr0 = e_top ? -2 : 0, sr1 = e_bot ? TH + 2 : TH, sg0 = e_lft ? -1 : 0, sg1 = e_rgt ? G + 1 : G;
             for (int item = tid; item < Cfg::G1H * GG; item += NT) {
-                const int rr = item / GG, g = item - rr * GG - 1;
-                const int r = rr - 2;
+                int r, g;
+                region_item<TH, G, 2>(item, r, g);                      // owned items first, then the halo ring
+                const int rr = r + 2;
                 const bool stat = r >= sr0 && r < sr1 && g >= sg0 && g < sg1;
                 f2 c[4];
                 ld4<PW>(Y1, (r + 6) * PW + 2 * (g + 3), c);
@@ -503,10 +530,10 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             for (int t = 0; t < 9; ++t) ws[t] = T->Ws[t];
             Bwd3Acc& acc = R2L_ACC(accs, tid);
             for (int item = tid; item < (TH + 2) * GG; item += NT) {
-                const int rr = item / GG, g = item - rr * GG - 1;
-                const int r = rr - 1;
+                int r, g;
+                region_item<TH, G, 1>(item, r, g);                      // owned items first, then the halo ring
                 const int qy = ty0 + r, qx = tx0 + 4 * g;
-                const bool owned = r >= 0 && r < TH && g >= 0 && g < G;
+                const bool owned = item < TH * G;
                 f2 c[4];
                 ld4<PW>(Y0, (r + 7) * PW + 2 * (g + 3), c);
                 f2 out[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
@@ -552,14 +579,27 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
                         for (int t = 0; t < 9; ++t) awq[cp][k][t] = T->AWq[2 * rp + cp][k][t];
             }
-            const int r_lo = e_top ? -1 : 0, r_hi = imin(TH + ((ty0 + TH == H) ? 1 : 0), H + 1 - ty0);
-            const int g_lo = e_lft ? -1 : 0, g_hi = G + ((tx0 + TW == W) ? 1 : 0);
-            const int r_first = r_lo + ((r_lo ^ rp) & 1);
-            const int nruns = g_hi - g_lo, nrows = r_hi > r_first ? (r_hi - r_first + 1) >> 1 : 0;
-            for (int i = slot; i < nrows * nruns; i += HALF) {
-                const int ri = nruns == G ? i / G : i / nruns;
-                const int g = g_lo + i - ri * nruns;
-                const int r = r_first + 2 * ri;
+            // items of this thread's row phase: the owned rows first (TH/2 x G, the same count for every thread), then
+            // the pad ring: row -1 (phase 1) / row TH (phase 0) and the runs -1 / G beside the owned rows
+            const int x_bot = ty0 + TH == H, x_rgt = tx0 + TW == W;
+            const int g_lo = e_lft ? -1 : 0, nruns = G + e_lft + x_rgt;
+            const int n_tb = (rp ? e_top : x_bot) ? nruns : 0;
+            const int n_ring = n_tb + (e_lft + x_rgt) * (TH / 2);
+            for (int i = slot; i < (TH / 2) * G + n_ring; i += HALF) {
+                int r, g;
+                if (i < (TH / 2) * G) {
+                    const int ri = i / G;
+                    r = rp + 2 * ri; g = i - ri * G;
+                } else {
+                    int h = i - (TH / 2) * G;
+                    if (h < n_tb) { r = rp ? -1 : TH; g = g_lo + h; }
+                    else {
+                        h -= n_tb;
+                        const int side = h / (TH / 2);
+                        r = rp + 2 * (h - side * (TH / 2));
+                        g = (side == 0 && e_lft) ? -1 : G;
+                    }
+                }
                 const int qy = ty0 + r, qx = tx0 + 4 * g;
                 // raw centres of the 4 sites (the reflected mosaic on pad sites)
                 f2 c[4];
@@ -599,11 +639,24 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                         }
                     }
                 }
-                if (Cfg::GRAW) st4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), graw[0], graw[1], graw[2], graw[3]);
+                if (Cfg::GRAW) {
+                    if (border) {
+                        st4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), graw[0], graw[1], graw[2], graw[3]);
+                    } else {                                            // no padding to fold: straight to global
+                        float* pa = a.graw + (size_t)b0 * plane + (size_t)qy * W + qx;
+                        f4 va; va.x = graw[0].x; va.y = graw[1].x; va.z = graw[2].x; va.w = graw[3].x;
+                        *reinterpret_cast<f4*>(pa) = va;
+                        if (!dup) {
+                            float* pb = a.graw + (size_t)b1 * plane + (size_t)qy * W + qx;
+                            f4 vb; vb.x = graw[0].y; vb.y = graw[1].y; vb.z = graw[2].y; vb.w = graw[3].y;
+                            *reinterpret_cast<f4*>(pb) = vb;
+                        }
+                    }
+                }
             }
         } }
         R2L_SYNC();
-        if (Cfg::GRAW) {
+        if (Cfg::GRAW && border) {
             // owned sites -> global, folding the reflect-1 pad ring onto rows/columns 1 and n-2 on the way
             { R2L_FOR_THREADS(NT) {
                 for (int item = tid; item < TH * G; item += NT) {
@@ -612,7 +665,7 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     if (qy >= H || qx >= W) continue;
                     f2 v[4];
                     ld4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), v);
-                    if (border && (qy == 1 || qy == H - 2 || qx == 0 || qx + 4 == W)) {
+                    if (qy == 1 || qy == H - 2 || qx == 0 || qx + 4 == W) {
                         for (int j = 0; j < 4; ++j) {
                             int ys[3], xs[3];
                             const int ny = preimages1(qy, H, ys), nx = preimages1(qx + j, W, xs);

@@ -127,3 +127,19 @@ def test_forward_v1_and_v2_agree_and_channel_statistics():
     o = v2.astype(np.float64)
     want = np.concatenate([o.sum(axis=(0, 2, 3)), (o * o).sum(axis=(0, 2, 3))])
     assert np.allclose(sums, want, rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape,n_cta,need_raw", [((3, 72, 136), 3, True), ((2, 64, 128), 3, True), ((1, 40, 72), 2, True),
+                                                  ((3, 96, 200), 5, True), ((2, 8, 8), 1, True), ((2, 37, 8), 3, True),
+                                                  ((2, 64, 128), 3, False), ((1, 101, 72), 4, True)])
+def test_vectorised_backward_multi_tile_shapes(shape, n_cta, need_raw):
+    """Third-generation backward (padded-domain phases + fold passes) on multi-tile / partial-tile / odd-batch shapes
+    against the fp64 oracle."""
+    raw = syn.smooth_scene(*shape, "drone", seed=sum(shape))
+    st = syn.perturbed_state(isp_oracle.default_state(syn.CAMERA_PRESETS["drone"]))
+    want, grads = isp_oracle.forward_backward(raw, st, grad_out="ramp", dtype=torch.float64)
+    g = isp_oracle.cotangent(tuple(want.shape), "ramp").numpy()
+    got = emu.backward(raw.numpy(), st, g, n_cta=n_cta, version=3, need_raw_grad=need_raw)
+    for k, v in got.items():
+        ref = grads[k].numpy()
+        assert maxabs(v.reshape(ref.shape), ref) <= 5e-6 * max(1.0, float(np.abs(ref).max())), (k, shape)
