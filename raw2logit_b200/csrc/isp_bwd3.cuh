@@ -176,6 +176,23 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         // (= column 1) and the run that ends at column W-1 writes pad column W (= column W-2).  Pad rows read the
         // mirrored source row.
         { R2L_FOR_THREADS(NT) {
+#ifndef R2L_HOST_EMU
+            // B4 reads the grad_out window (rows -4..TH+3 of 3 channels x 2 images) long after this point: start
+            // pulling its 128-byte lines into L2 now so those loads are L2 hits
+            {
+                constexpr int LPR = TW * 4 / 128;                      // lines per owned row
+                const int rows = Cfg::FH, nl = rows * 6 * LPR;
+                for (int i = tid; i < nl; i += NT) {
+                    const int l = i % LPR, pr = i / LPR, pk = pr % 6, rr = pr / 6;
+                    const int gy = ty0 - 4 + rr, gx = tx0 + l * 32;
+                    const int img = pk < 3 ? b0 : b1, k = pk < 3 ? pk : pk - 3;
+                    if (gy >= 0 && gy < H && gx < W) {
+                        const float* ptr = a.gout + ((size_t)img * 3 + k) * plane + (size_t)gy * W + gx;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+                    }
+                }
+            }
+#endif
             constexpr int Q = PW / 4;
             for (int i = tid; i < Cfg::RH * Q; i += NT) {
                 const int ly = i / Q, lq = i - ly * Q;
@@ -416,15 +433,15 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                         const f2 l2 = mk2(fast_log2(cl.x), fast_log2(cl.y));
                         const f2 ex = mul2s(l2, invg1);
                         const f2 e = mk2(fast_exp2(ex.x), fast_exp2(ex.y));
-                        f2 Gv = mk2(gak[j], gbk[j]);
+                        // scalar products: the loaded values are consumed where they are needed, not re-paired early
+                        float Ga = gak[j], Gb = gbk[j];
                         if (Cfg::TAIL) {
                             const f2 o = mul2vv(cl, e);
                             const float ya = fmaf_(o.x + adk[j], t_sc, t_sh), yb = fmaf_(o.y + adk[j], t_sc, t_sh);
-                            Gv = mk2(t_gs * (Gv.x - t_c1 - t_c2 * ya), t_gs * (Gv.y - t_c1 - t_c2 * yb));
-                            if (!valid) Gv = mk2(0.f, 0.f);
-                            if (dup) Gv.y = 0.f;
+                            Ga = valid ? t_gs * (Ga - t_c1 - t_c2 * ya) : 0.f;
+                            Gb = (valid && !dup) ? t_gs * (Gb - t_c1 - t_c2 * yb) : 0.f;
                         }
-                        const f2 ge = mul2vv(Gv, e);
+                        const f2 ge = mk2(Ga * e.x, Gb * e.y);
                         if (owned) acc.sg = fma2vv(ge, mul2vv(cl, l2), acc.sg);
                         // clamp backward mask (inclusive at both ends): the value passed iff clamping left it unchanged
                         const f2 gr = mk2(rgb.x == cl.x ? ge.x : 0.f, rgb.y == cl.y ? ge.y : 0.f);

@@ -1,0 +1,62 @@
+"""Data parallelism for the ISP path: one process per GPU, the image batch sharded across ranks, and ONE collective
+per step -- an all-reduce of every gradient (the 132 ISP scalars ride in the same flat bucket as the task-model
+gradients, never as 7 latency-bound 4..324-byte messages).  The reference has no distributed code
+(single process, ``gpus=1``, train.py:362); this is the new build's sharding of its batch dimension.
+
+Forward needs no communication (images are independent units); BatchNorm statistics stay per replica, as in the
+single-GPU reference (no SyncBN).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_batch(x, rank, world):
+    """Rank ``rank`` of ``world`` takes images rank, rank+world, ... of the global batch (first dimension)."""
+    return x[rank::world]
+
+
+def flat_gradients(parameters):
+    """All existing gradients of ``parameters`` in one contiguous vector, plus the (param, offset, numel) layout."""
+    params = [p for p in parameters if p.grad is not None]
+    layout, n = [], 0
+    for p in params:
+        layout.append((p, n, p.numel()))
+        n += p.numel()
+    if not params:
+        return None, layout
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    return flat, layout
+
+
+def allreduce_gradients(parameters, world=None, group=None, average=True):
+    """One all-reduce over the flat gradient bucket; writes the reduced values back into ``p.grad``.
+
+    Returns the number of elements communicated (0 when nothing had a gradient).  With ``world == 1`` (or no
+    initialised process group) it is a no-op."""
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    flat, layout = flat_gradients(parameters)
+    if flat is None:
+        return 0
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(world)
+        for p, off, n in layout:
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+    return flat.numel()
+
+
+def data_parallel_step(model, batch, optimizer=None, rank=0, world=1, group=None):
+    """One training step of ``model`` (a ``raw2logit_b200.model.LitModel``) on this rank's shard of ``batch``:
+    forward, loss, backward, single-bucket gradient all-reduce, optional optimizer step.  Returns the local loss."""
+    x, y = batch
+    x, y = shard_batch(x, rank, world), shard_batch(y, rank, world)
+    for p in model.parameters():
+        p.grad = None
+    loss = model.update_step((x, y))
+    loss.backward()
+    allreduce_gradients(model.parameters(), world=world, group=group)
+    if optimizer is not None:
+        optimizer.step()
+    return loss.detach()

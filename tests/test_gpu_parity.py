@@ -293,3 +293,33 @@ def test_vectorised_backward_agrees_with_generic_backward(shape, bn):
             assert maxabs(pa, pb) <= 2e-5 * scale, (shape, bn, x0.dtype, need_raw, maxabs(pa, pb))
             if need_raw:
                 assert maxabs(ra, rb) <= 1e-6 * max(1.0, rb.abs().max().item()), (shape, bn)
+
+
+@pytest.mark.parametrize("cot", ["mean", "ramp"])
+def test_track_stages_mode_matches_reference_stages_and_stage_gradients(cot):
+    """track_stages=True (model.track_images, reference model.py:229-254): every stage tensor, its .grad, the output
+    (incl. the YUV->RGB->YUV round trip of pipeline_torch.py:197-200) and all gradients against the golden fixture."""
+    from processing.pipeline_torch import ParametrizedProcessing
+    c = GoldenCase("stages_pert")
+    mod = ParametrizedProcessing(track_stages=True, batch_norm_output=False)
+    mod.load_state_dict(c.state, strict=True)
+    mod = mod.cuda()
+    x = c.raw.cuda().requires_grad_(True)
+    out = mod(x)
+    assert list(mod.stages) == ["demosaic", "color_correct", "sharpening", "gaussian", "clipped", "gamma_correct"]
+    assert mod.buffer["processed_rgb"] is out
+    out.backward(isp_oracle.cotangent(tuple(out.shape), cot).cuda())
+    assert maxabs(out.detach().cpu().numpy(), c.f32["out"]) <= FWD_ATOL
+    for name, t in mod.stages.items():
+        assert maxabs(t.detach().cpu().numpy(), c.f32[f"stage.{name}"]) <= FWD_ATOL, name
+        ref = c.f64[f"stagegrad.{cot}.{name}"]
+        assert t.grad is not None, name
+        assert maxabs(t.grad.cpu().numpy(), ref) <= GRAD_ATOL * max(1.0, float(np.abs(ref).max())), name
+    named = dict(mod.named_parameters())
+    for k in isp_oracle.PARAM_KEYS:
+        assert maxabs(named[k].grad.cpu().numpy(), c.f64[f"grad.{cot}.{k}"]) <= GRAD_ATOL, k
+    ref = c.f64[f"grad.{cot}.raw"]
+    assert maxabs(x.grad.cpu().numpy(), ref) <= GRAD_ATOL * max(1.0, float(np.abs(ref).max()))
+    # without a raw gradient the stages are populated but nothing is retained (pipeline_torch.py:219-221)
+    out2 = mod(c.raw.cuda())
+    assert len(mod.stages) == 6 and out2.shape == out.shape
