@@ -21,6 +21,7 @@
 //     predicates only.
 // Shapes the fold pass cannot serve from one tile (a last tile row/column of <= 4 sites) go to the generic kernel.
 #pragma once
+#include <type_traits>
 #include "isp_fwd2.cuh"
 
 namespace r2l {
@@ -466,34 +467,52 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             // statistic domain: owned rectangle, extended over the pad ring on image-border sides (products vanish
             // beyond the ring because gY2 is zero outside the image)
             const int sr0 = e_top ? -2 : 0, sr1 = e_bot ? TH + 2 : TH, sg0 = e_lft ? -1 : 0, sg1 = e_rgt ? G + 1 : G;
-            for (int item = tid; item < Cfg::G1H * GG; item += NT) {
-                int r, g;
-                region_item<TH, G, 2>(item, r, g);                      // owned items first, then the halo ring
-                const int rr = r + 2;
-                const bool stat = r >= sr0 && r < sr1 && g >= sg0 && g < sg1;
-                f2 c[4];
-                ld4<PW>(Y1, (r + 6) * PW + 2 * (g + 3), c);
-                f2 out[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
+            // one work item = NR runs of one row processed in lockstep (runs g and g + G/2): the statistic chains then
+            // run over 4*NR sites before their horizontal add, and two independent windows are in flight per thread
+            auto b5 = [&](auto NRc, int r, int g, bool stat) {
+                constexpr int NR = decltype(NRc)::value;
+                f2 c[NR][4], out[NR][4];
+#pragma unroll
+                for (int u = 0; u < NR; ++u) {
+                    ld4<PW>(Y1, (r + 6) * PW + 2 * (g + u * (G / 2) + 3), c[u]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) out[u][j] = mk2(0.f, 0.f);
+                }
 #pragma unroll
                 for (int d = 0; d < 5; ++d) {
-                    f2 row[8];                                          // gY2 row q.y - 2 + d, columns q.x - 2 .. q.x + 5
-                    ld8<PN>(PG, (r + 2 + d) * PN + 2 * (g + 2), row);
+                    f2 row[NR][8];                                      // gY2 row q.y - 2 + d, columns q.x - 2 .. q.x + 5
+#pragma unroll
+                    for (int u = 0; u < NR; ++u) ld8<PN>(PG, (r + 2 + d) * PN + 2 * (g + u * (G / 2) + 2), row[u]);
                     const int aa = 4 - d;                               // tap row whose transpose reaches this row
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int u = 0; u < NR; ++u)
 #pragma unroll
-                        for (int bb = 0; bb < 5; ++bb) out[j] = fma2s(row[j + 4 - bb], wg[aa * 5 + bb], out[j]);
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int bb = 0; bb < 5; ++bb) out[u][j] = fma2s(row[u][j + 4 - bb], wg[aa * 5 + bb], out[u][j]);
                     if (stat) {
 #pragma unroll
                         for (int bb = 0; bb < 5; ++bb) {
-                            f2 t = mul2vv(c[0], row[4 - bb]);
+                            f2 t = mul2vv(c[0][0], row[0][4 - bb]);
 #pragma unroll
-                            for (int j = 1; j < 4; ++j) t = fma2vv(c[j], row[j + 4 - bb], t);
+                            for (int u = 0; u < NR; ++u)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (u | j) t = fma2vv(c[u][j], row[u][j + 4 - bb], t);
                             acc.wg[aa * 5 + bb] += t.x + t.y;
                         }
                     }
                 }
-                st4<PN>(GY1, rr * PN + 2 * (g + 2), out[0], out[1], out[2], out[3]);
+#pragma unroll
+                for (int u = 0; u < NR; ++u)
+                    st4<PN>(GY1, (r + 2) * PN + 2 * (g + u * (G / 2) + 2), out[u][0], out[u][1], out[u][2], out[u][3]);
+            };
+            for (int item = tid; item < TH * (G / 2); item += NT)       // owned rectangle: one paired item per thread
+                b5(std::integral_constant<int, 2>(), item / (G / 2), item % (G / 2), true);
+            for (int item = TH * G + tid; item < Cfg::G1H * GG; item += NT) {      // halo ring, single runs
+                int r, g;
+                region_item<TH, G, 2>(item, r, g);
+                b5(std::integral_constant<int, 1>(), r, g, r >= sr0 && r < sr1 && g >= sg0 && g < sg1);
             }
         } }
         R2L_SYNC();
@@ -546,38 +565,56 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
             for (int t = 0; t < 9; ++t) ws[t] = T->Ws[t];
             Bwd3Acc& acc = R2L_ACC(accs, tid);
-            for (int item = tid; item < (TH + 2) * GG; item += NT) {
-                int r, g;
-                region_item<TH, G, 1>(item, r, g);                      // owned items first, then the halo ring
-                const int qy = ty0 + r, qx = tx0 + 4 * g;
-                const bool owned = item < TH * G;
-                f2 c[4];
-                ld4<PW>(Y0, (r + 7) * PW + 2 * (g + 3), c);
-                f2 out[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
+            auto b6 = [&](auto NRc, int r, int g, bool owned) {
+                constexpr int NR = decltype(NRc)::value;
+                f2 c[NR][4], out[NR][4];
+#pragma unroll
+                for (int u = 0; u < NR; ++u) {
+                    ld4<PW>(Y0, (r + 7) * PW + 2 * (g + u * (G / 2) + 3), c[u]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) out[u][j] = mk2(0.f, 0.f);
+                }
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    f2 row[6];                                          // gY1 row q.y - 1 + d, columns q.x - 1 .. q.x + 4
-                    ld6<PN>(GY1, (r + 1 + d) * PN + 2 * (g + 2), row);
+                    f2 row[NR][6];                                      // gY1 row q.y - 1 + d, columns q.x - 1 .. q.x + 4
+#pragma unroll
+                    for (int u = 0; u < NR; ++u) ld6<PN>(GY1, (r + 1 + d) * PN + 2 * (g + u * (G / 2) + 2), row[u]);
                     const int aa = 2 - d;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int u = 0; u < NR; ++u)
 #pragma unroll
-                        for (int bb = 0; bb < 3; ++bb) out[j] = fma2s(row[j + 2 - bb], ws[aa * 3 + bb], out[j]);
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int bb = 0; bb < 3; ++bb) out[u][j] = fma2s(row[u][j + 2 - bb], ws[aa * 3 + bb], out[u][j]);
                     if (owned) {
 #pragma unroll
                         for (int bb = 0; bb < 3; ++bb) {
-                            f2 t = mul2vv(c[0], row[2 - bb]);
+                            f2 t = mul2vv(c[0][0], row[0][2 - bb]);
 #pragma unroll
-                            for (int j = 1; j < 4; ++j) t = fma2vv(c[j], row[j + 2 - bb], t);
+                            for (int u = 0; u < NR; ++u)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (u | j) t = fma2vv(c[u][j], row[u][j + 2 - bb], t);
                             acc.ws[aa * 3 + bb] += t.x + t.y;
                         }
                     }
                 }
-                if (qy < 0 || qy >= H || qx < 0 || qx >= W) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) out[j] = mk2(0.f, 0.f);
+                for (int u = 0; u < NR; ++u) {
+                    const int qy = ty0 + r, qx = tx0 + 4 * (g + u * (G / 2));
+                    if (qy < 0 || qy >= H || qx < 0 || qx >= W) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) out[u][j] = mk2(0.f, 0.f);
+                    }
+                    st4<PN>(PG, (r + 4) * PN + 2 * (g + u * (G / 2) + 2), out[u][0], out[u][1], out[u][2], out[u][3]);
                 }
-                st4<PN>(PG, (r + 4) * PN + 2 * (g + 2), out[0], out[1], out[2], out[3]);
+            };
+            for (int item = tid; item < TH * (G / 2); item += NT)       // owned rectangle: one paired item per thread
+                b6(std::integral_constant<int, 2>(), item / (G / 2), item % (G / 2), true);
+            for (int item = TH * G + tid; item < (TH + 2) * GG; item += NT) {      // halo ring, single runs
+                int r, g;
+                region_item<TH, G, 1>(item, r, g);
+                b6(std::integral_constant<int, 1>(), r, g, false);
             }
         } }
         R2L_SYNC();
@@ -657,9 +694,13 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     }
                 }
                 if (Cfg::GRAW) {
-                    if (border) {
+                    // runs that receive folded pad contributions (rows 1 / H-2, first / last run of the image) and the
+                    // pad ring itself go through shared memory; everything else goes straight to global
+                    const bool ring = r < 0 || r >= TH || g < 0 || g >= G;
+                    const bool special = qy == 1 || qy == H - 2 || qx == 0 || qx + 4 == W;
+                    if (border && (ring || special || qy >= H || qx >= W)) {
                         st4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), graw[0], graw[1], graw[2], graw[3]);
-                    } else {                                            // no padding to fold: straight to global
+                    } else {
                         float* pa = a.graw + (size_t)b0 * plane + (size_t)qy * W + qx;
                         f4 va; va.x = graw[0].x; va.y = graw[1].x; va.z = graw[2].x; va.w = graw[3].x;
                         *reinterpret_cast<f4*>(pa) = va;
@@ -680,9 +721,10 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     const int r = item / G, g = item - r * G;
                     const int qy = ty0 + r, qx = tx0 + 4 * g;
                     if (qy >= H || qx >= W) continue;
+                    if (!(qy == 1 || qy == H - 2 || qx == 0 || qx + 4 == W)) continue;     // stored by B7 already
                     f2 v[4];
                     ld4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), v);
-                    if (qy == 1 || qy == H - 2 || qx == 0 || qx + 4 == W) {
+                    {
                         for (int j = 0; j < 4; ++j) {
                             int ys[3], xs[3];
                             const int ny = preimages1(qy, H, ys), nx = preimages1(qx + j, W, xs);

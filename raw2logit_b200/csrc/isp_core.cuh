@@ -660,25 +660,26 @@ template <class Cfg> R2L_HD int thread_par(int tid) { return (((tid / Cfg::TW) &
 // ---------------------------------------------------------------------------------------------------------
 // finish: statistics -> the 132 parameter gradients (runs in one small CTA, double precision)
 // ---------------------------------------------------------------------------------------------------------
-// S: the kNumStats sums over all CTAs.  T: tables of the same launch.  Writes grad e of the flat vector.
-R2L_HD float finish_grad(int e, const double* S, const Tables* T) {
+// S: the kNumStats sums over all CTAs.  T: tables of the same launch.
+// Qr[k][par][t] = sum g_yuv[k](p) * (raw - black)(p + tap t) over sites p of phase par
+R2L_HD double finish_qr(const double* S, const Tables* T, int k, int par, int t) {
+    return S[stat_q_index(k, par, t)] - (double)T->bl[par_tap(par, t)] * S[stat_p_index(k, par)];
+}
+// Sc[m][c] = sum_p g_c[m](p) * d[c](p), g_c = M1^T g_yuv, d = demosaiced RGB before white balance
+R2L_HD double finish_sc(const double* S, const Tables* T, int m, int c) {
+    double s = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        double tkc = 0.0;
+        for (int par = 0; par < 4; ++par)
+            for (int t = 0; t < 9; ++t)
+                tkc += (double)T->wd[(c * 3 + ch_of(par_tap(par, t))) * 9 + t] * finish_qr(S, T, k, par, t);
+        s += (double)T->m1[k * 3 + m] * tkc;
+    }
+    return s;
+}
+// grad e of the flat vector; Sc9 = the nine finish_sc values [m][c] (computed once by the caller)
+R2L_HD float finish_grad_sc(int e, const double* S, const Tables* T, const double* Sc9) {
     const double ln2 = 0.693147180559945309417;
-    // Qr[k][par][t] = sum g_yuv[k](p) * (raw - black)(p + tap t) over sites p of phase par
-    auto Qr = [&](int k, int par, int t) -> double {
-        return S[stat_q_index(k, par, t)] - (double)T->bl[par_tap(par, t)] * S[stat_p_index(k, par)];
-    };
-    // Sc[m][c] = sum_p g_c[m](p) * d[c](p), g_c = M1^T g_yuv, d = demosaiced RGB before white balance
-    auto Sc = [&](int m, int c) -> double {
-        double s = 0.0;
-        for (int k = 0; k < 3; ++k) {
-            double tkc = 0.0;
-            for (int par = 0; par < 4; ++par)
-                for (int t = 0; t < 9; ++t)
-                    tkc += (double)T->wd[(c * 3 + ch_of(par_tap(par, t))) * 9 + t] * Qr(k, par, t);
-            s += (double)T->m1[k * 3 + m] * tkc;
-        }
-        return s;
-    };
     if (e < 4) {                      // black_level[par']
         double s = 0.0;
         for (int par = 0; par < 4; ++par)
@@ -690,12 +691,12 @@ R2L_HD float finish_grad(int e, const double* S, const Tables* T) {
     if (e < 7) {                      // white_balance[c] = sum_m CCM[m][c] * Sc[m][c]
         const int c = e - 4;
         double s = 0.0;
-        for (int m = 0; m < 3; ++m) s += (double)T->ccm[m * 3 + c] * Sc(m, c);
+        for (int m = 0; m < 3; ++m) s += (double)T->ccm[m * 3 + c] * Sc9[m * 3 + c];
         return (float)s;
     }
     if (e < 16) {                     // colour_correction[m][c] = Sc[m][c] * wb[c]
         const int m = (e - 7) / 3, c = (e - 7) - 3 * m;
-        return (float)(Sc(m, c) * (double)T->wb[c]);
+        return (float)(Sc9[m * 3 + c] * (double)T->wb[c]);
     }
     if (e < 17) {                     // gamma: -(1/g^2) * ln2 * sum G o log2(cl)
         const double ig = (double)T->invg;
@@ -706,11 +707,16 @@ R2L_HD float finish_grad(int e, const double* S, const Tables* T) {
         double s = 0.0;
         for (int par = 0; par < 4; ++par)
             if (ch_of(par_tap(par, t)) == c)
-                for (int k = 0; k < 3; ++k) s += (double)T->A[k * 3 + kd] * Qr(k, par, t);
+                for (int k = 0; k < 3; ++k) s += (double)T->A[k * 3 + kd] * finish_qr(S, T, k, par, t);
         return (float)s;
     }
     if (e < 107) return (float)S[kStatWs + (e - 98)];
     return (float)S[kStatWg + (e - 107)];
+}
+R2L_HD float finish_grad(int e, const double* S, const Tables* T) {
+    double Sc9[9];
+    for (int i = 0; i < 9; ++i) Sc9[i] = (e >= 4 && e < 16) ? finish_sc(S, T, i / 3, i % 3) : 0.0;
+    return finish_grad_sc(e, S, T, Sc9);
 }
 
 // ---------------------------------------------------------------------------------------------------------
