@@ -4,10 +4,12 @@
 #include "isp_fwd2.cuh"
 #include "isp_bwd2.cuh"
 #include "isp_bwd3.cuh"
+#include "isp_fwd3.cuh"
 
 namespace r2l {
 using FwdDefault = FwdCfg<32, 64, 256>;          // v1 (scalar) -- kept for the emulation cross-check only
-using Fwd2Default = Fwd2Cfg<32, 64, 256>;        // v2: image pairs, FFMA2, register micro-tiles
+using Fwd2Default = Fwd2Cfg<32, 64, 256>;        // v2: image pairs, FFMA2, register micro-tiles (any shape)
+using Fwd3Default = Fwd3Cfg<32, 64, 256>;        // v3: border rules on the data, four barriers per tile (W % 4 == 0)
 using BwdNoRaw = BwdCfg<32, 64, 256, false>;     // v1 (scalar) -- emulation cross-check only
 using Bwd2NoRaw = Bwd2Cfg<32, 64, 256, false>;
 using Bwd2WithRaw = Bwd2Cfg<32, 64, 256, true>;

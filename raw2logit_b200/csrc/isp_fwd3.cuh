@@ -1,0 +1,397 @@
+// isp_fwd3.cuh -- third-generation fused forward: the border rules live on the data, four barriers per tile.
+//
+// Reference: ParametrizedProcessing.forward, pipeline_torch.py:175-225.  Same float2 (image A, image B) planes, FFMA2
+// arithmetic and chunk de-interleaved rows as isp_fwd2.cuh; what changes is that no fix-up pass (and none of their
+// barriers) is left -- the second generation spent ~15 % of its samples waiting at the barriers of three tiny
+// border passes (profiles/r03_summary.md):
+//   * F1 de-interleaves the TMA-staged raw window and mirrors it on the way (reflect-1 of the mosaic, :233): pad
+//     rows read the mirrored staging row, pad columns -1 / W are written by the first / last run inside the image;
+//   * F2 stores Y0 as exact zero outside the image (the sharpen conv zero-pads, :162);
+//   * F3 evaluates pad rows of Y1 at the mirrored row and lets the border-adjacent run write the pad columns
+//     (the Gaussian reflect-pads the sharpened plane, :165/:202);
+//   * F4 = Gaussian on 2x4 register micro-tiles + YUV->RGB + clip + gamma [+ additive] [+ affine | channel sums].
+// Work items are 1x4 site runs entirely inside or outside the image: needs W % 4 == 0 (other shapes: isp_fwd2.cuh).
+#pragma once
+#include "isp_fwd2.cuh"
+
+namespace r2l {
+
+template <int TH_, int TW_, int NT_> struct Fwd3Cfg {
+    static constexpr int TH = TH_, TW = TW_, NT = NT_;
+    static constexpr int P = TW + 16;                 // row pitch (sites) of the haloed planes; column index = gx - x0 + 8
+    static constexpr int RH = TH + 8, Y0H = TH + 6, Y1H = TH + 4;
+    static constexpr int G = TW / 4;                  // 4-site runs per tile row
+    static constexpr int kTableFloats = (sizeof(Tables2) + 15) / 16 * 4;
+    static constexpr int kXR = RH * P, kY0 = Y0H * P, kUV = TH * TW;          // sizes in float2 sites
+    static constexpr int kSites = kXR + kY0 + 2 * kUV;
+    static constexpr size_t kPlaneBytes = (size_t)kTableFloats * 4 + (size_t)kSites * 8;
+    static constexpr size_t kStageOffset = (kPlaneBytes + 127) / 128 * 128;       // TMA destination: 128-byte aligned
+    static constexpr size_t kStageBytes = (size_t)2 * RH * P * 4;                 // [image][row][P] of the raw element
+    static constexpr size_t kSmemBytes = kPlaneBytes;
+    static constexpr size_t kSmemBytesTma = kStageOffset + kStageBytes + 16;      // + staging + mbarrier
+    static constexpr int HALF = NT / 2;
+    static_assert(TW % 8 == 0 && TH % 2 == 0 && NT % 64 == 0, "warp-parity mapping");
+    static_assert(Y1H * P <= kXR, "Y1 aliases the raw window");
+};
+
+inline bool fwd3_shape_ok(int H, int W) { return (W % 4) == 0 && H >= 4 && W >= 8; }
+
+// TAIL: additive layer and/or affine epilogue may be present (runtime pointers); STATS: per-channel sums for the
+// train-mode BatchNorm tail (additive may be present, affine is applied by a later pass)
+template <class Cfg, typename RawT, bool STATS, bool TAIL, bool TMA>
+R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid, float* smem, const void* tmap = nullptr) {
+    constexpr int TH = Cfg::TH, TW = Cfg::TW, NT = Cfg::NT, P = Cfg::P, G = Cfg::G, HALF = Cfg::HALF;
+    constexpr int GG = G + 2;                                     // runs -1 .. G
+    Tables2* T2 = reinterpret_cast<Tables2*>(smem);
+    Tables* T = &T2->base;
+    f2* XR = reinterpret_cast<f2*>(smem + Cfg::kTableFloats);    // raw window, later Y1
+    f2* Y0 = XR + Cfg::kXR;
+    f2* U = Y0 + Cfg::kY0;
+    f2* V = U + Cfg::kUV;
+    f2* Y1 = XR;
+#ifdef R2L_HOST_EMU
+    std::vector<ChanAcc> cacc(NT);
+    for (int i = 0; i < NT; ++i) for (int k = 0; k < 6; ++k) cacc[i].s[k] = 0.f;
+#else
+    ChanAcc cacc;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cacc.s[k] = 0.f;
+#endif
+    // planes start finite: never-written pad columns and out-of-image sites are read by don't-care items
+    { R2L_FOR_THREADS(NT) {
+        for (int i = tid; i < Cfg::kSites; i += NT) XR[i] = mk2(0.f, 0.f);
+    } }
+    R2L_BUILD_TABLES(NT, a.P, T)
+    { R2L_FOR_THREADS(NT) { build_tables2_extra(tid, NT, T2); } }
+    R2L_SYNC();
+
+    const int H = a.H, W = a.W;
+    const size_t plane = (size_t)H * W;
+#ifndef R2L_HOST_EMU
+    RawT* stage = reinterpret_cast<RawT*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset + Cfg::kStageBytes);
+    uint32_t tma_phase = 0;
+    constexpr uint32_t kTmaBytes = 2u * Cfg::RH * P * sizeof(RawT);
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(mbar, 1);
+            if (cta < grid.n) {
+                int pb0, pb1, py0, px0;
+                decode_pair_tile(grid, cta, TH, TW, a.B, pb0, pb1, py0, px0);
+                tma_load_3d(stage, tmap, px0 - 8, py0 - 4, pb0, mbar, kTmaBytes);
+            }
+        }
+        __syncthreads();
+    }
+#endif
+    for (int tile = cta; tile < grid.n; tile += n_cta) {
+        int b0, b1, ty0, tx0;
+        decode_pair_tile(grid, tile, TH, TW, a.B, b0, b1, ty0, tx0);
+        const bool dup = b1 == b0;
+        const RawT* imgA = static_cast<const RawT*>(a.raw) + (size_t)b0 * plane;
+        const RawT* imgB = static_cast<const RawT*>(a.raw) + (size_t)b1 * plane;
+#ifndef R2L_HOST_EMU
+        if (TMA) {
+            mbar_wait(mbar, tma_phase);      // this tile's raw window has landed in the staging buffer
+            tma_phase ^= 1u;
+        }
+#endif
+        // ---- F1: raw window (rows -4..TH+3, runs -2..G+1) de-interleaved into float2 sites, mirrored ---------------
+        { R2L_FOR_THREADS(NT) {
+            constexpr int Q = P / 4;
+            for (int i = tid; i < Cfg::RH * Q; i += NT) {
+                const int ly = i / Q, lq = i - ly * Q;
+                const int gy = ty0 - 4 + ly, gx = tx0 - 8 + 4 * lq;
+                if (gx < 0 || gx >= W) continue;
+                const int sy = mirror_clamped(gy, H);
+                float va[4], vb[4];
+#ifndef R2L_HOST_EMU
+                if (TMA) {
+                    const int sl = imin(imax(sy - (ty0 - 4), 0), Cfg::RH - 1);
+                    const RawT* sa = stage + sl * P + 4 * lq;
+                    const RawT* sb = sa + Cfg::RH * P;
+                    if (sizeof(RawT) == 4) {
+                        const f4 xa = *reinterpret_cast<const f4*>(sa);
+                        const f4 xb = *reinterpret_cast<const f4*>(sb);
+                        va[0] = xa.x; va[1] = xa.y; va[2] = xa.z; va[3] = xa.w;
+                        vb[0] = xb.x; vb[1] = xb.y; vb[2] = xb.z; vb[3] = xb.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            va[j] = __fdiv_rn((float)sa[j], a.denom);
+                            vb[j] = __fdiv_rn((float)sb[j], a.denom);
+                        }
+                    }
+                } else
+#endif
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        va[j] = RawLoad<RawT>::get(imgA + (size_t)sy * W + gx + j, a.denom);
+                        vb[j] = RawLoad<RawT>::get(imgB + (size_t)sy * W + gx + j, a.denom);
+                    }
+                }
+                st4<P>(XR, ly * P + 2 * lq, mk2(va[0], vb[0]), mk2(va[1], vb[1]), mk2(va[2], vb[2]), mk2(va[3], vb[3]));
+                if (gx == 0 && lq > 0) XR[ly * P + phys<P>(4 * lq - 1)] = mk2(va[1], vb[1]);
+                if (gx + 4 == W && lq < Q - 1) XR[ly * P + phys<P>(4 * lq + 4)] = mk2(va[2], vb[2]);
+            }
+        } }
+        R2L_SYNC();
+#ifndef R2L_HOST_EMU
+        if (TMA && threadIdx.x == 0) {
+            const int next = tile + n_cta;
+            if (next < grid.n) {
+                int nb0, nb1, ny0, nx0;
+                decode_pair_tile(grid, next, TH, TW, a.B, nb0, nb1, ny0, nx0);
+                tma_load_3d(stage, tmap, nx0 - 8, ny0 - 4, nb0, mbar, kTmaBytes);
+            }
+        }
+#endif
+
+        // ---- F2: Y0 (exact zero outside the image) on rows -3..TH+2, runs -1..G; U and V on the tile ---------------
+        { R2L_FOR_THREADS(NT) {
+            const int rp = (tid >> 5) & 1, slot = ((tid >> 6) << 5) | (tid & 31);
+            float w[2][3][9], cb[2][3];
+            {
+                const f4* src = reinterpret_cast<const f4*>(T2->awrow[rp]);
+                float tmp[56];
+#pragma unroll
+                for (int q = 0; q < 14; ++q) { const f4 v = src[q]; tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w; }
+#pragma unroll
+                for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) w[cp][k][t] = tmp[cp * 27 + k * 9 + t];
+#pragma unroll
+                for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) cb[cp][k] = T2->cbrow[rp][cp * 3 + k];
+            }
+            // owned rows of this thread's CFA row phase: TH/2 rows x G runs
+            for (int i = slot; i < (TH / 2) * G; i += HALF) {
+                const int ri = i / G, g = i - ri * G;
+                const int r = rp + 2 * ri, q = 2 + g;
+                f2 acc[4][3];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) acc[j][k] = mk2(-cb[j & 1][k], -cb[j & 1][k]);
+#pragma unroll
+                for (int aa = 0; aa < 3; ++aa) {
+                    f2 in[6];
+                    ld6<P>(XR, (r + 3 + aa) * P + 2 * q, in);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+                            for (int k = 0; k < 3; ++k)
+                                acc[j][k] = fma2s(in[j + bb], w[j & 1][k][aa * 3 + bb], acc[j][k]);
+                }
+                if (ty0 + r >= H || tx0 + 4 * g >= W) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j][0] = mk2(0.f, 0.f);
+                }
+                st4<P>(Y0, (r + 3) * P + 2 * q, acc[0][0], acc[1][0], acc[2][0], acc[3][0]);
+                st4<TW>(U, r * TW + 2 * g, acc[0][1], acc[1][1], acc[2][1], acc[3][1]);
+                st4<TW>(V, r * TW + 2 * g, acc[0][2], acc[1][2], acc[2][2], acc[3][2]);
+            }
+        } }
+        // luma-only ring: rows -3..-1 and TH..TH+2 x runs -1..G, plus runs -1 and G of the tile rows
+        { R2L_FOR_THREADS(NT) {
+            constexpr int kTopBot = 6 * GG, kSide = 2 * TH;
+            for (int item = tid; item < kTopBot + kSide; item += NT) {
+                int ry, g;
+                if (item < kTopBot) {
+                    const int rr = item / GG;
+                    g = item - rr * GG - 1;
+                    ry = rr < 3 ? rr - 3 : TH + rr - 3;
+                } else {
+                    const int s = item - kTopBot;
+                    ry = s >> 1;
+                    g = (s & 1) ? G : -1;
+                }
+                const int hp = ry & 1;
+                float wy[2][9];
+                {
+                    const f4* src = reinterpret_cast<const f4*>(T2->awy[hp]);
+                    float tmp[20];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) { const f4 v = src[q]; tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w; }
+#pragma unroll
+                    for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) wy[cp][t] = tmp[cp * 9 + t];
+                }
+                const float cb0 = T2->cbrow[hp][0], cb1 = T2->cbrow[hp][3];
+                const int q = 2 + g;
+                f2 acc[4] = {mk2(-cb0, -cb0), mk2(-cb1, -cb1), mk2(-cb0, -cb0), mk2(-cb1, -cb1)};
+#pragma unroll
+                for (int aa = 0; aa < 3; ++aa) {
+                    f2 in[6];
+                    ld6<P>(XR, (ry + 3 + aa) * P + 2 * q, in);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int bb = 0; bb < 3; ++bb) acc[j] = fma2s(in[j + bb], wy[j & 1][aa * 3 + bb], acc[j]);
+                }
+                const int gy = ty0 + ry, gx = tx0 + 4 * g;
+                if (gy < 0 || gy >= H || gx < 0 || gx >= W) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] = mk2(0.f, 0.f);
+                }
+                st4<P>(Y0, (ry + 3) * P + 2 * q, acc[0], acc[1], acc[2], acc[3]);
+            }
+        } }
+        R2L_SYNC();
+
+        // ---- F3: Y1 = sharpen(Y0) on rows -2..TH+1, runs -1..G (1x4 runs); overwrites the raw window -----------------
+        { R2L_FOR_THREADS(NT) {
+            float ws[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) ws[t] = T->Ws[t];
+            for (int item = tid; item < Cfg::Y1H * GG; item += NT) {
+                const int rr = item / GG, g = item - rr * GG - 1;
+                const int gy = ty0 - 2 + rr, gx = tx0 + 4 * g;
+                if (gx < 0 || gx >= W) continue;
+                int sr = rr;                                           // Y0 rows sr .. sr+2 <-> image rows gy-1 .. gy+1
+                if ((gy < 0 && gy >= -2) || (gy >= H && gy <= H + 1)) sr = mirror(gy, H) - (ty0 - 2);
+                const int q = 2 + g;
+                f2 acc[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
+#pragma unroll
+                for (int aa = 0; aa < 3; ++aa) {
+                    f2 in[6];
+                    ld6<P>(Y0, (sr + aa) * P + 2 * q, in);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int bb = 0; bb < 3; ++bb) acc[j] = fma2s(in[j + bb], ws[aa * 3 + bb], acc[j]);
+                }
+                st4<P>(Y1, rr * P + 2 * q, acc[0], acc[1], acc[2], acc[3]);
+                if (gx == 0) { Y1[rr * P + phys<P>(4 * q - 1)] = acc[1]; Y1[rr * P + phys<P>(4 * q - 2)] = acc[2]; }
+                if (gx + 4 == W) { Y1[rr * P + phys<P>(4 * q + 4)] = acc[2]; Y1[rr * P + phys<P>(4 * q + 5)] = acc[1]; }
+            }
+        } }
+        R2L_SYNC();
+
+        // ---- F4: Gaussian (2x4 runs) + YUV->RGB + clip + gamma [+ additive] [+ affine | sums] -> global ----------------
+        { R2L_FOR_THREADS(NT) {
+            float wg[25], m2[9];
+#pragma unroll
+            for (int t = 0; t < 25; ++t) wg[t] = T->Wg[t];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) m2[t] = T->M2[t];
+            const float invg = T->invg;
+            float sc[3] = {1.f, 1.f, 1.f}, sh[3] = {0.f, 0.f, 0.f};
+            bool has_aff = false;
+            if (TAIL && a.affine) {
+                has_aff = true;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { sc[k] = a.affine[k]; sh[k] = a.affine[3 + k]; }
+            }
+            for (int item = tid; item < (TH / 2) * G; item += NT) {
+                const int r0 = 2 * (item / G), g = item % G;
+                const int q = 2 + g;
+                const int gx = tx0 + 4 * g;
+                f2 acc[2][4];
+#pragma unroll
+                for (int o = 0; o < 2; ++o)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[o][j] = mk2(0.f, 0.f);
+#pragma unroll
+                for (int ir = 0; ir < 6; ++ir) {
+                    f2 in[8];
+                    ld8<P>(Y1, (r0 + ir) * P + 2 * q, in);        // Y1 row index of image row (ty0 + r0 - 2 + ir)
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        const int aa = ir - o;
+                        if (aa >= 0 && aa < 5) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int bb = 0; bb < 5; ++bb) acc[o][j] = fma2s(in[j + bb], wg[aa * 5 + bb], acc[o][j]);
+                        }
+                    }
+                }
+                if (gx >= W) continue;
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {
+                    const int gy = ty0 + r0 + o;
+                    if (gy >= H) continue;
+                    f2 u[4], v[4];
+                    ld4<TW>(U, (r0 + o) * TW + 2 * g, u);
+                    ld4<TW>(V, (r0 + o) * TW + 2 * g, v);
+                    const size_t pix = (size_t)gy * W + gx;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        float oa[4], ob[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const f2 rr = fma2s(v[j], m2[k * 3 + 2], fma2s(u[j], m2[k * 3 + 1], mul2s(acc[o][j], m2[k * 3])));
+                            const float ca = fminf(fmaxf(rr.x, kClipLo), kClipHi);
+                            const float cbv = fminf(fmaxf(rr.y, kClipLo), kClipHi);
+                            oa[j] = fast_exp2(invg * fast_log2(ca));
+                            ob[j] = fast_exp2(invg * fast_log2(cbv));
+                        }
+                        if ((TAIL || STATS) && a.additive) {
+                            const f4 ad = *reinterpret_cast<const f4*>(a.additive + (size_t)k * plane + pix);
+                            oa[0] += ad.x; oa[1] += ad.y; oa[2] += ad.z; oa[3] += ad.w;
+                            ob[0] += ad.x; ob[1] += ad.y; ob[2] += ad.z; ob[3] += ad.w;
+                        }
+                        if (STATS) {
+                            ChanAcc& cs = R2L_ACC(cacc, tid);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                cs.s[k] += oa[j];
+                                cs.s[3 + k] = fmaf_(oa[j], oa[j], cs.s[3 + k]);
+                                if (!dup) {
+                                    cs.s[k] += ob[j];
+                                    cs.s[3 + k] = fmaf_(ob[j], ob[j], cs.s[3 + k]);
+                                }
+                            }
+                        }
+                        if (TAIL && has_aff) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { oa[j] = fmaf_(oa[j], sc[k], sh[k]); ob[j] = fmaf_(ob[j], sc[k], sh[k]); }
+                        }
+                        f4 va; va.x = oa[0]; va.y = oa[1]; va.z = oa[2]; va.w = oa[3];
+                        *reinterpret_cast<f4*>(a.out + ((size_t)b0 * 3 + k) * plane + pix) = va;
+                        if (!dup) {
+                            f4 vb; vb.x = ob[0]; vb.y = ob[1]; vb.z = ob[2]; vb.w = ob[3];
+                            *reinterpret_cast<f4*>(a.out + ((size_t)b1 * 3 + k) * plane + pix) = vb;
+                        }
+                    }
+                }
+            }
+        } }
+        R2L_SYNC();   // planes are rewritten by the next tile
+    }
+    if (STATS) {
+        float* part = a.chan_partials + (size_t)cta * kChanPitch;
+#ifdef R2L_HOST_EMU
+        for (int k = 0; k < 6; ++k) {
+            double sum = 0.0;
+            for (int i = 0; i < NT; ++i) sum += cacc[i].s[k];
+            part[k] = (float)sum;
+        }
+#else
+        constexpr int NW = NT / 32;
+        float* red = smem + Cfg::kTableFloats;
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const float v = warp_sum_all(cacc.s[k]);
+            if (lane == 0) red[warp * 6 + k] = v;
+        }
+        __syncthreads();
+        if (tid < 6) {
+            float sum = 0.f;
+            for (int w = 0; w < NW; ++w) sum += red[w * 6 + tid];
+            part[tid] = sum;
+        }
+#endif
+    }
+}
+
+}  // namespace r2l

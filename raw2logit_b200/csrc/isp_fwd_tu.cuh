@@ -36,8 +36,38 @@ static int launch_forward_t(const FwdArgs& a, cudaStream_t st, int* grid_used) {
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);
 }
 
+// third generation (TMA-fed, W % 4 == 0)
+template <class Cfg, typename RawT, bool STATS, bool TAIL>
+__global__ void __launch_bounds__(Cfg::NT, 2) isp_forward3_kernel(FwdArgs a, TileGrid grid,
+                                                                  const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float smem[];
+    fwd3_cta<Cfg, RawT, STATS, TAIL, true>(blockIdx.x, gridDim.x, a, grid, smem, &tmap);
+}
+
+template <class Cfg, typename RawT, bool STATS, bool TAIL>
+static int launch_forward3_t(const FwdArgs& a, cudaStream_t st, int* grid_used) {
+    const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);     // tiles of image pairs
+    CUtensorMap tmap;
+    if (!make_raw_tensor_map(&tmap, a.raw, (int)sizeof(RawT), a.B, a.H, a.W, Cfg::P, Cfg::RH)) return kNotServed;
+    int g = 0;
+    int rc = persistent_grid(isp_forward3_kernel<Cfg, RawT, STATS, TAIL>, Cfg::NT, Cfg::kSmemBytesTma, grid.n, &g);
+    if (rc != R2L_OK) return rc;
+    isp_forward3_kernel<Cfg, RawT, STATS, TAIL><<<g, Cfg::NT, Cfg::kSmemBytesTma, st>>>(a, grid, tmap);
+    if (grid_used) *grid_used = g;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? R2L_OK : cuda_fail(e);
+}
+
 template <typename RawT>
 static int launch_forward_impl(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used) {
+    const char* force = getenv("R2L_ISP_FORCE_GENERIC");            // debugging knob: second-generation kernel
+    if (!(force && force[0] == '1') && fwd3_shape_ok(a.H, a.W) && aligned(a.out, 16) && aligned(a.additive, 16)) {
+        int rc;
+        if (stats) rc = launch_forward3_t<Fwd3Default, RawT, true, false>(a, st, grid_used);
+        else if (a.additive || a.affine) rc = launch_forward3_t<Fwd3Default, RawT, false, true>(a, st, grid_used);
+        else rc = launch_forward3_t<Fwd3Default, RawT, false, false>(a, st, grid_used);
+        if (rc != kNotServed) return rc;
+    }
     return stats ? launch_forward_t<Fwd2Default, RawT, true>(a, st, grid_used)
                  : launch_forward_t<Fwd2Default, RawT, false>(a, st, grid_used);
 }

@@ -97,18 +97,28 @@ __global__ void bn_backward_finish_kernel(const float* partials, const float* af
     gtail[12 + c] = affine[3 + c];              // ysh
 }
 
-// statistics of all CTAs -> 132 parameter gradients.  One CTA of 1024 threads: the per-CTA partial sums are read with
-// every load independent and in flight at once (the first version walked them one dependent load at a time and
-// spent 16 us on L2 latency), summed in double in a fixed order (bit-reproducible), then mapped to the gradients.
+// statistics of all CTAs -> 132 parameter gradients.  One CTA of 1024 threads.  The per-CTA partial sums are read with
+// every load independent and in flight at once, summed in double in a fixed order (bit-reproducible); the chain
+// rule from the collapsed-table statistics back to black level / white balance / colour matrix / demosaic taps
+// (finish_grad_sc, isp_core.cuh) is spread over warps: its long sums (36 and 27 terms) are one term per lane.
 constexpr int kFinishThreads = 1024;
 constexpr int kFinishSegs = kFinishThreads / kStatPitch;        // 6 segments of CTAs
+__device__ __forceinline__ double warp_sum_all_f64(double v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 __global__ void __launch_bounds__(kFinishThreads) isp_backward_finish_kernel(Params P, const float* partials,
                                                                              int n_cta, float* grads) {
     __shared__ Tables T;
     __shared__ double Sseg[kFinishSegs][kStatPitch];
     __shared__ double S[kNumStats];
+    __shared__ double Qr[108];          // [k][par][t]
+    __shared__ double Tkc[9];           // [k][c] = sum_{par,t} wd[c][ch(par_tap)][t] * Qr[k][par][t]
+    __shared__ double Gbl[4];
     __shared__ double Sc9[9];
-    const int s = threadIdx.x % kStatPitch, seg = threadIdx.x / kStatPitch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = tid % kStatPitch, seg = tid / kStatPitch;
     double sum = 0.0;
     if (seg < kFinishSegs && s < kNumStats) {
         int c = seg;
@@ -123,16 +133,44 @@ __global__ void __launch_bounds__(kFinishThreads) isp_backward_finish_kernel(Par
     }
     if (seg < kFinishSegs) Sseg[seg][s] = sum;
     R2L_BUILD_TABLES(kFinishThreads, P, &T)                         // ends with a barrier
-    if (threadIdx.x < kNumStats) {
+    if (tid < kNumStats) {
         double t = 0.0;
 #pragma unroll
-        for (int g = 0; g < kFinishSegs; ++g) t += Sseg[g][threadIdx.x];
-        S[threadIdx.x] = t;
+        for (int g = 0; g < kFinishSegs; ++g) t += Sseg[g][tid];
+        S[tid] = t;
     }
     __syncthreads();
-    if (threadIdx.x < 9) Sc9[threadIdx.x] = finish_sc(S, &T, threadIdx.x / 3, threadIdx.x % 3);
+    if (tid < 108) { const int k = tid / 36, r = tid - 36 * k; Qr[tid] = finish_qr(S, &T, k, r / 9, r % 9); }
     __syncthreads();
-    if (threadIdx.x < R2L_NUM_PARAM_GRADS) grads[threadIdx.x] = finish_grad_sc(threadIdx.x, S, &T, Sc9);
+    if (warp < 9) {                                                  // Tkc[k][c]: 36 terms, lanes take (par, t)
+        const int k = warp / 3, c = warp - 3 * k;
+        double v = 0.0;
+        for (int i = lane; i < 36; i += 32) {
+            const int par = i / 9, t = i - 9 * par;
+            v += (double)T.wd[(c * 3 + ch_of(par_tap(par, t))) * 9 + t] * Qr[k * 36 + i];
+        }
+        v = warp_sum_all_f64(v);
+        if (lane == 0) Tkc[warp] = v;
+    } else if (warp < 13) {                                          // black_level[e]: 27 terms, lanes take (t, k)
+        const int e = warp - 9;
+        double v = 0.0;
+        if (lane < 27) {
+            const int t = lane / 3, k = lane - 3 * t, par = par_tap(e, t);      // par_tap(par, t) == e (an involution)
+            v = (double)T.AW[par][k][t] * S[stat_p_index(k, par)];
+        }
+        v = warp_sum_all_f64(v);
+        if (lane == 0) Gbl[e] = -v;
+    }
+    __syncthreads();
+    if (tid < 9) {                                                   // Sc[m][c] = sum_k M1[k][m] * Tkc[k][c]
+        const int m = tid / 3, c = tid - 3 * m;
+        double v = 0.0;
+        for (int k = 0; k < 3; ++k) v += (double)T.m1[k * 3 + m] * Tkc[k * 3 + c];
+        Sc9[tid] = v;
+    }
+    __syncthreads();
+    if (tid < 4) grads[tid] = (float)Gbl[tid];
+    else if (tid < R2L_NUM_PARAM_GRADS) grads[tid] = finish_grad_sc(tid, S, &T, Sc9);
 }
 
 template <typename RawT>

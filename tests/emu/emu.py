@@ -13,6 +13,7 @@ DEPS = [SRC, os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_core.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_fwd2.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd2.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd3.cuh"),
+        os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_fwd3.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_config.h"), os.path.join(ROOT, "include", "r2l_isp.h")]
 
 PARAM_FIELDS = ["black_level", "white_balance", "colour_correction", "gamma_correct", "debayer.weight",
@@ -57,7 +58,7 @@ def _params(state):
     return p, keep
 
 
-def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0, version=2, chan_sums=None):
+def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0, version=3, chan_sums=None):
     raw = np.ascontiguousarray(raw)
     dtype = 1 if raw.dtype == np.uint16 else 0
     if dtype == 0:

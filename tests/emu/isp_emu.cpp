@@ -26,6 +26,16 @@ static void run_forward_v1(const FwdArgs& a, int n_cta) {
     for (int cta = 0; cta < n_cta; ++cta) fwd_cta<Cfg, RawT, false>(cta, n_cta, a, grid, smem.data());
 }
 
+template <typename RawT, bool STATS, bool TAIL>
+static void run_forward3(const FwdArgs& a, int n_cta) {
+    using Cfg = Fwd3Default;
+    const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);
+    std::vector<float> smem(Cfg::kSmemBytes / 4 + 4);
+    float* base = smem.data();
+    while (reinterpret_cast<uintptr_t>(base) % 16) ++base;
+    for (int cta = 0; cta < n_cta; ++cta) fwd3_cta<Cfg, RawT, STATS, TAIL, false>(cta, n_cta, a, grid, base);
+}
+
 template <class Cfg, typename RawT, bool STATS>
 static void run_forward(const FwdArgs& a, int n_cta) {
     const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);
@@ -90,6 +100,25 @@ int emu_isp_forward(const void* raw, int raw_dtype, float denom, int B, int H, i
     if (version == 1) {
         if (raw_dtype == R2L_F32) run_forward_v1<FwdDefault, float>(a, n_cta);
         else run_forward_v1<FwdDefault, uint16_t>(a, n_cta);
+    } else if (version == 3 && fwd3_shape_ok(H, W)) {                 // same dispatch rule as the CUDA launcher
+        std::vector<float> partials((size_t)n_cta * kChanPitch, 0.f);
+        if (chan_sums) a.chan_partials = partials.data();
+        const bool tailf = a.additive || a.affine;
+        if (raw_dtype == R2L_F32) {
+            if (chan_sums) run_forward3<float, true, false>(a, n_cta);
+            else if (tailf) run_forward3<float, false, true>(a, n_cta);
+            else run_forward3<float, false, false>(a, n_cta);
+        } else {
+            if (chan_sums) run_forward3<uint16_t, true, false>(a, n_cta);
+            else if (tailf) run_forward3<uint16_t, false, true>(a, n_cta);
+            else run_forward3<uint16_t, false, false>(a, n_cta);
+        }
+        if (chan_sums)
+            for (int k = 0; k < 6; ++k) {
+                double s = 0.0;
+                for (int c = 0; c < n_cta; ++c) s += partials[(size_t)c * kChanPitch + k];
+                chan_sums[k] = s;
+            }
     } else if (chan_sums) {
         std::vector<float> partials((size_t)n_cta * kChanPitch, 0.f);
         a.chan_partials = partials.data();

@@ -143,3 +143,29 @@ def test_vectorised_backward_multi_tile_shapes(shape, n_cta, need_raw):
     for k, v in got.items():
         ref = grads[k].numpy()
         assert maxabs(v.reshape(ref.shape), ref) <= 5e-6 * max(1.0, float(np.abs(ref).max())), (k, shape)
+
+
+@pytest.mark.parametrize("shape,n_cta", [((3, 72, 136), 3), ((2, 64, 128), 2), ((1, 40, 72), 2), ((3, 96, 200), 5),
+                                         ((2, 8, 8), 1), ((2, 37, 8), 3), ((1, 101, 72), 4), ((1, 5, 12), 1)])
+def test_forward_v3_multi_tile_shapes(shape, n_cta):
+    """Third-generation forward (border rules on the data, no fix-up passes) against the fp64 oracle and against the
+    second generation, with the additive layer + affine epilogue and the channel sums of the BatchNorm tail."""
+    raw = syn.smooth_scene(*shape, "drone", seed=sum(shape))
+    st = syn.perturbed_state(isp_oracle.default_state(syn.CAMERA_PRESETS["drone"]))
+    want, _ = isp_oracle.forward(raw.double(), isp_oracle.cast_state(st, torch.float64), dtype=torch.float64)
+    v3 = emu.forward(raw.numpy(), st, n_cta=n_cta, version=3)
+    assert maxabs(v3, want) <= 2e-6
+    v2 = emu.forward(raw.numpy(), st, n_cta=n_cta, version=2)
+    assert maxabs(v3, v2) <= 1e-6
+    g = torch.Generator().manual_seed(1)
+    add = (0.01 * torch.randn(3, shape[1], shape[2], generator=g)).numpy()
+    aff = np.asarray([1.5, 0.5, 2.0, -0.1, 0.2, 0.3], dtype=np.float32)
+    t3 = emu.forward(raw.numpy(), st, additive=add, affine=aff, n_cta=n_cta, version=3)
+    t2 = emu.forward(raw.numpy(), st, additive=add, affine=aff, n_cta=n_cta, version=2)
+    assert maxabs(t3, t2) <= 2e-6
+    s3, s2 = np.zeros(6), np.zeros(6)
+    o3 = emu.forward(raw.numpy(), st, additive=add, n_cta=n_cta, version=3, chan_sums=s3)
+    emu.forward(raw.numpy(), st, additive=add, n_cta=n_cta, version=2, chan_sums=s2)
+    o = o3.astype(np.float64)
+    assert np.allclose(s3, np.concatenate([o.sum(axis=(0, 2, 3)), (o * o).sum(axis=(0, 2, 3))]), rtol=1e-5)
+    assert np.allclose(s3, s2, rtol=1e-5)
