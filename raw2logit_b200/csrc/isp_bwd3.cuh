@@ -194,43 +194,11 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 }
             }
 #endif
-            constexpr int Q = PW / 4;
-            for (int i = tid; i < Cfg::RH * Q; i += NT) {
-                const int ly = i / Q, lq = i - ly * Q;
-                const int gy = ty0 - 8 + ly, gx = tx0 - 12 + 4 * lq;
-                if (gx < 0 || gx >= W) continue;
-                const int sy = mirror_clamped(gy, H);
-                float va[4], vb[4];
-#ifndef R2L_HOST_EMU
-                if (TMA) {
-                    const int sl = imin(imax(sy - (ty0 - 8), 0), Cfg::RH - 1);
-                    const RawT* sa = stage + sl * SP + 4 * lq + (SX - 12);
-                    const RawT* sb = sa + Cfg::RH * SP;
-                    if (sizeof(RawT) == 4) {
-                        const f4 xa = *reinterpret_cast<const f4*>(sa);
-                        const f4 xb = *reinterpret_cast<const f4*>(sb);
-                        va[0] = xa.x; va[1] = xa.y; va[2] = xa.z; va[3] = xa.w;
-                        vb[0] = xb.x; vb[1] = xb.y; vb[2] = xb.z; vb[3] = xb.w;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            va[j] = __fdiv_rn((float)sa[j], a.denom);
-                            vb[j] = __fdiv_rn((float)sb[j], a.denom);
-                        }
-                    }
-                } else
+#ifdef R2L_HOST_EMU
+            const RawT* stage = nullptr;
+            constexpr int SX = 12, SP = PW;
 #endif
-                {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        va[j] = RawLoad<RawT>::get(imgA + (size_t)sy * W + gx + j, a.denom);
-                        vb[j] = RawLoad<RawT>::get(imgB + (size_t)sy * W + gx + j, a.denom);
-                    }
-                }
-                st4<PW>(XR, ly * PW + 2 * lq, mk2(va[0], vb[0]), mk2(va[1], vb[1]), mk2(va[2], vb[2]), mk2(va[3], vb[3]));
-                if (gx == 0 && lq > 0) site3<PW>(XR, ly, 4 * lq - 1) = mk2(va[1], vb[1]);
-                if (gx + 4 == W && lq < Q - 1) site3<PW>(XR, ly, 4 * lq + 4) = mk2(va[2], vb[2]);
-            }
+            phase_deinterleave<PW, Cfg::RH, 8, 12, SP, SX - 12, NT, RawT, TMA>(tid, XR, stage, imgA, imgB, a.denom, ty0, tx0, H, W);
         } }
         R2L_SYNC();
 #ifndef R2L_HOST_EMU

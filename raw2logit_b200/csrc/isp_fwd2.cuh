@@ -65,6 +65,59 @@ template <int P> R2L_HD void ld4(const f2* pl, int eb, f2 v[4]) {
     ld2(pl + eb, v[0], v[1]); ld2(pl + eb + P / 2, v[2], v[3]);
 }
 
+
+// ---- raw window -> float2 plane (image A, image B), mirrored on the way (third-generation kernels) ----------------
+// The plane has RH rows x P sites, its site (0,0) is image site (ty0 - ROFF, tx0 - COFF).  The source is the TMA
+// staging buffer [image][RH][SP] whose column 0 is image column tx0 - COFF - SOFF (TMA = true) or global memory.
+// Runs (4 sites) outside the image are not stored; pad rows read the mirrored source row (reflect-1 of the mosaic,
+// pipeline_torch.py:233: -1 -> 1, H -> H-2); pad columns -1 / W are written by the first / last run of the image.
+// The outermost run on each side (beyond the halo any consumer reads) is skipped.
+template <int P, int RH, int ROFF, int COFF, int SP, int SOFF, int NT, typename RawT, bool TMA>
+R2L_HD void phase_deinterleave(int tid, f2* XR, const RawT* stage, const RawT* imgA, const RawT* imgB, float denom,
+                               int ty0, int tx0, int H, int W) {
+    constexpr int Q = P / 4, QI = Q - 2;
+    for (int i = tid; i < RH * QI; i += NT) {
+        const int ly = i / QI, lq = i - ly * QI + 1;
+        const int gy = ty0 - ROFF + ly, gx = tx0 - COFF + 4 * lq;
+        if ((unsigned)gx >= (unsigned)W) continue;
+        int sy = gy;
+        if ((unsigned)gy >= (unsigned)H) sy = mirror_clamped(gy, H);
+        float va[4], vb[4];
+#ifndef R2L_HOST_EMU
+        if (TMA) {
+            int sl = ly;
+            if (sy != gy) sl = imin(imax(sy - (ty0 - ROFF), 0), RH - 1);
+            const RawT* sa = stage + sl * SP + 4 * lq + SOFF;
+            const RawT* sb = sa + RH * SP;
+            if (sizeof(RawT) == 4) {
+                const f4 xa = *reinterpret_cast<const f4*>(sa);
+                const f4 xb = *reinterpret_cast<const f4*>(sb);
+                va[0] = xa.x; va[1] = xa.y; va[2] = xa.z; va[3] = xa.w;
+                vb[0] = xb.x; vb[1] = xb.y; vb[2] = xb.z; vb[3] = xb.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    va[j] = __fdiv_rn((float)sa[j], denom);
+                    vb[j] = __fdiv_rn((float)sb[j], denom);
+                }
+            }
+        } else
+#endif
+        {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                va[j] = RawLoad<RawT>::get(imgA + (size_t)sy * W + gx + j, denom);
+                vb[j] = RawLoad<RawT>::get(imgB + (size_t)sy * W + gx + j, denom);
+            }
+        }
+        const int eb = ly * P + 2 * lq, ob = eb + P / 2;
+        st2(XR + eb, mk2(va[0], vb[0]), mk2(va[1], vb[1]));
+        st2(XR + ob, mk2(va[2], vb[2]), mk2(va[3], vb[3]));
+        if (gx == 0) XR[ob - 1] = mk2(va[1], vb[1]);                  // site 4*lq - 1 (pad column -1 = column 1)
+        if (gx + 4 == W) XR[eb + 2] = mk2(va[2], vb[2]);              // site 4*lq + 4 (pad column W = column W-2)
+    }
+}
+
 #ifndef R2L_HOST_EMU
 // ---- TMA (cp.async.bulk.tensor) + mbarrier: the raw window of both images is fetched by the copy engine into a
 // staging buffer while the previous tile is still being computed ------------------------------------------------
