@@ -317,6 +317,9 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             float ws[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) ws[t] = T->Ws[t];
+            const f2* __restrict__ Y0r = Y0;                            // B3 only reads Y0 and only writes Y1
+            f2* __restrict__ Y1w = Y1;
+#pragma unroll 2
             for (int item = tid; item < Cfg::Y1H * (G + 4); item += NT) {
                 const int rr = item / (G + 4), g = item - rr * (G + 4) - 2;
                 const int gy = ty0 - 6 + rr, gx = tx0 + 4 * g;
@@ -327,15 +330,15 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
                 for (int aa = 0; aa < 3; ++aa) {
                     f2 in[6];
-                    ld6<PW>(Y0, (sr + aa) * PW + 2 * (g + 3), in);
+                    ld6<PW>(Y0r, (sr + aa) * PW + 2 * (g + 3), in);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
 #pragma unroll
                         for (int bb = 0; bb < 3; ++bb) acc[j] = fma2s(in[j + bb], ws[aa * 3 + bb], acc[j]);
                 }
-                st4<PW>(Y1, rr * PW + 2 * (g + 3), acc[0], acc[1], acc[2], acc[3]);
-                if (gx == 0) { site3<PW>(Y1, rr, 4 * (g + 3) - 1) = acc[1]; site3<PW>(Y1, rr, 4 * (g + 3) - 2) = acc[2]; }
-                if (gx + 4 == W) { site3<PW>(Y1, rr, 4 * (g + 3) + 4) = acc[2]; site3<PW>(Y1, rr, 4 * (g + 3) + 5) = acc[1]; }
+                st4<PW>(Y1w, rr * PW + 2 * (g + 3), acc[0], acc[1], acc[2], acc[3]);
+                if (gx == 0) { site3<PW>(Y1w, rr, 4 * (g + 3) - 1) = acc[1]; site3<PW>(Y1w, rr, 4 * (g + 3) - 2) = acc[2]; }
+                if (gx + 4 == W) { site3<PW>(Y1w, rr, 4 * (g + 3) + 4) = acc[2]; site3<PW>(Y1w, rr, 4 * (g + 3) + 5) = acc[1]; }
             }
         } }
         R2L_SYNC();

@@ -73,9 +73,10 @@ template <int P> R2L_HD void ld4(const f2* pl, int eb, f2 v[4]) {
 // pipeline_torch.py:233: -1 -> 1, H -> H-2); pad columns -1 / W are written by the first / last run of the image.
 // The outermost run on each side (beyond the halo any consumer reads) is skipped.
 template <int P, int RH, int ROFF, int COFF, int SP, int SOFF, int NT, typename RawT, bool TMA>
-R2L_HD void phase_deinterleave(int tid, f2* XR, const RawT* stage, const RawT* imgA, const RawT* imgB, float denom,
-                               int ty0, int tx0, int H, int W) {
+R2L_HD void phase_deinterleave(int tid, f2* __restrict__ XR, const RawT* __restrict__ stage, const RawT* imgA,
+                               const RawT* imgB, float denom, int ty0, int tx0, int H, int W) {
     constexpr int Q = P / 4, QI = Q - 2;
+#pragma unroll 2
     for (int i = tid; i < RH * QI; i += NT) {
         const int ly = i / QI, lq = i - ly * QI + 1;
         const int gy = ty0 - ROFF + ly, gx = tx0 - COFF + 4 * lq;
