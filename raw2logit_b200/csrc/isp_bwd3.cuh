@@ -129,34 +129,31 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         for (int i = 0; i < kBwd3AccFloats; ++i) z[i] = 0.f;
     }
 #endif
+    const int H = a.H, W = a.W;
+    const size_t plane = (size_t)H * W;
+#ifndef R2L_HOST_EMU
+    // the first tile's raw window is requested before anything else so the copy overlaps the CTA prologue
+    RawT* stage = reinterpret_cast<RawT*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset + Cfg::kStageBytes);
+    uint32_t tma_phase = 0;
+    constexpr int SX = sizeof(RawT) == 2 ? 16 : 12, SP = sizeof(RawT) == 2 ? PW + 8 : PW;
+    constexpr uint32_t kTmaBytes = 2u * Cfg::RH * SP * sizeof(RawT);
+    if (TMA && threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        if (cta < grid.n) {
+            int pb0, pb1, py0, px0;
+            decode_pair_tile(grid, cta, TH, TW, a.B, pb0, pb1, py0, px0);
+            tma_load_3d(stage, tmap, px0 - SX, py0 - 8, pb0, mbar, kTmaBytes);
+        }
+    }
+#endif
     // planes start finite: never-written pad columns and out-of-image sites are read by don't-care items
     { R2L_FOR_THREADS(NT) {
         for (int i = tid; i < Cfg::kSites; i += NT) XR[i] = mk2(0.f, 0.f);
     } }
     R2L_BUILD_TABLES(NT, a.P, T)
     { R2L_FOR_THREADS(NT) { build_tables2_extra(tid, NT, T2); } }
-    R2L_SYNC();
-
-    const int H = a.H, W = a.W;
-    const size_t plane = (size_t)H * W;
-#ifndef R2L_HOST_EMU
-    RawT* stage = reinterpret_cast<RawT*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset + Cfg::kStageBytes);
-    uint32_t tma_phase = 0;
-    constexpr int SX = sizeof(RawT) == 2 ? 16 : 12, SP = sizeof(RawT) == 2 ? PW + 8 : PW;
-    constexpr uint32_t kTmaBytes = 2u * Cfg::RH * SP * sizeof(RawT);
-    if (TMA) {
-        if (threadIdx.x == 0) {
-            mbar_init(mbar, 1);
-            if (cta < grid.n) {
-                int pb0, pb1, py0, px0;
-                decode_pair_tile(grid, cta, TH, TW, a.B, pb0, pb1, py0, px0);
-                tma_load_3d(stage, tmap, px0 - SX, py0 - 8, pb0, mbar, kTmaBytes);
-            }
-        }
-        __syncthreads();
-    }
-#endif
+    R2L_SYNC();                                  // also publishes the mbarrier initialisation to every thread
     for (int tile = cta; tile < grid.n; tile += n_cta) {
         int b0, b1, ty0, tx0;
         decode_pair_tile(grid, tile, TH, TW, a.B, b0, b1, ty0, tx0);
@@ -738,12 +735,15 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         }
 #else
     {
+        static_assert(kBwd3AccFloats == 96, "three groups of 32 running sums");
         const float* src = reinterpret_cast<const float*>(&accs);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-        for (int i = 0; i < kBwd3AccFloats; ++i) {
-            const float v = warp_sum_all(src[i]);
-            if (lane == 0) red[warp * RP + i] = v;
+        for (int grp = 0; grp < 3; ++grp) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = src[grp * 32 + i];
+            red[warp * RP + grp * 32 + lane] = warp_transpose_sum32(v);
         }
     }
 #endif

@@ -74,6 +74,22 @@ __device__ __forceinline__ float warp_sum_same_parity(float v) {
     for (int o = 16; o >= 2; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Sums 32 per-lane values across the warp at once: on return lane L holds the warp total of v[L].  31 shuffles
+// instead of 160 (each step exchanges one half of the still-live values with the partner lane), fixed order.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float send = up ? v[i] : v[i + o];
+            const float keep = up ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
 #endif
 R2L_HD int imin(int a, int b) { return a < b ? a : b; }
 R2L_HD int imax(int a, int b) { return a > b ? a : b; }

@@ -57,33 +57,30 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
 #pragma unroll
     for (int k = 0; k < 6; ++k) cacc.s[k] = 0.f;
 #endif
+    const int H = a.H, W = a.W;
+    const size_t plane = (size_t)H * W;
+#ifndef R2L_HOST_EMU
+    // the first tile's raw window is requested before anything else so the copy overlaps the CTA prologue
+    RawT* stage = reinterpret_cast<RawT*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset + Cfg::kStageBytes);
+    uint32_t tma_phase = 0;
+    constexpr uint32_t kTmaBytes = 2u * Cfg::RH * P * sizeof(RawT);
+    if (TMA && threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        if (cta < grid.n) {
+            int pb0, pb1, py0, px0;
+            decode_pair_tile(grid, cta, TH, TW, a.B, pb0, pb1, py0, px0);
+            tma_load_3d(stage, tmap, px0 - 8, py0 - 4, pb0, mbar, kTmaBytes);
+        }
+    }
+#endif
     // planes start finite: never-written pad columns and out-of-image sites are read by don't-care items
     { R2L_FOR_THREADS(NT) {
         for (int i = tid; i < Cfg::kSites; i += NT) XR[i] = mk2(0.f, 0.f);
     } }
     R2L_BUILD_TABLES(NT, a.P, T)
     { R2L_FOR_THREADS(NT) { build_tables2_extra(tid, NT, T2); } }
-    R2L_SYNC();
-
-    const int H = a.H, W = a.W;
-    const size_t plane = (size_t)H * W;
-#ifndef R2L_HOST_EMU
-    RawT* stage = reinterpret_cast<RawT*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset + Cfg::kStageBytes);
-    uint32_t tma_phase = 0;
-    constexpr uint32_t kTmaBytes = 2u * Cfg::RH * P * sizeof(RawT);
-    if (TMA) {
-        if (threadIdx.x == 0) {
-            mbar_init(mbar, 1);
-            if (cta < grid.n) {
-                int pb0, pb1, py0, px0;
-                decode_pair_tile(grid, cta, TH, TW, a.B, pb0, pb1, py0, px0);
-                tma_load_3d(stage, tmap, px0 - 8, py0 - 4, pb0, mbar, kTmaBytes);
-            }
-        }
-        __syncthreads();
-    }
-#endif
+    R2L_SYNC();                                  // also publishes the mbarrier initialisation to every thread
     for (int tile = cta; tile < grid.n; tile += n_cta) {
         int b0, b1, ty0, tx0;
         decode_pair_tile(grid, tile, TH, TW, a.B, b0, b1, ty0, tx0);

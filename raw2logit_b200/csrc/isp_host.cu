@@ -17,13 +17,20 @@ namespace r2l {
 // exactly like torch (momentum update, unbiased variance for the running estimate).
 __global__ void bn_finish_kernel(const float* partials, int n_cta, double count, float momentum, float eps,
                                  float* running_mean, float* running_var, float* affine) {
-    const int c = threadIdx.x;
+    // one warp per channel; lanes stride over the per-CTA partial sums (independent loads), fixed-order fp64 reduction
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (c >= 3) return;
     double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < n_cta; ++i) {
+    for (int i = lane; i < n_cta; i += 32) {
         s1 += (double)partials[(size_t)i * kChanPitch + c];
         s2 += (double)partials[(size_t)i * kChanPitch + 3 + c];
     }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane != 0) return;
     const double mean = s1 / count;
     double var = s2 / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -83,13 +90,19 @@ __global__ void __launch_bounds__(256) bn_backward_stats_kernel(const float* gy,
     }
 }
 __global__ void bn_backward_finish_kernel(const float* partials, const float* affine, double count, float* gtail) {
-    const int c = threadIdx.x;
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (c >= 3) return;
     double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < kBnBwdBlocks; ++i) {
+    for (int i = lane; i < kBnBwdBlocks; i += 32) {
         s1 += (double)partials[((size_t)c * kBnBwdBlocks + i) * 2];
         s2 += (double)partials[((size_t)c * kBnBwdBlocks + i) * 2 + 1];
     }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane != 0) return;
     gtail[c] = affine[c];                       // gs  = 1/sqrt(var+eps)
     gtail[3 + c] = (float)(s1 / count);         // c1  = mean(gy)
     gtail[6 + c] = (float)(s2 / count);         // c2  = mean(gy * yhat)
@@ -121,15 +134,17 @@ __global__ void __launch_bounds__(kFinishThreads) isp_backward_finish_kernel(Par
     const int s = tid % kStatPitch, seg = tid / kStatPitch;
     double sum = 0.0;
     if (seg < kFinishSegs && s < kNumStats) {
-        int c = seg;
-        for (; c + 7 * kFinishSegs < n_cta; c += 8 * kFinishSegs) {
-            float v[8];
+        // up to 32 CTAs per thread and round, every load issued before the first add (one L2 round trip per round)
+        for (int c0 = seg; c0 < n_cta; c0 += 32 * kFinishSegs) {
+            float v[32];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(partials + (size_t)(c + u * kFinishSegs) * kStatPitch + s);
+            for (int u = 0; u < 32; ++u) {
+                const int c = c0 + u * kFinishSegs;
+                v[u] = c < n_cta ? __ldcg(partials + (size_t)c * kStatPitch + s) : 0.f;
+            }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) sum += (double)v[u];
+            for (int u = 0; u < 32; ++u) sum += (double)v[u];
         }
-        for (; c < n_cta; c += kFinishSegs) sum += (double)__ldcg(partials + (size_t)c * kStatPitch + s);
     }
     if (seg < kFinishSegs) Sseg[seg][s] = sum;
     R2L_BUILD_TABLES(kFinishThreads, P, &T)                         // ends with a barrier
@@ -384,7 +399,7 @@ int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominat
     int g = 0;
     rc = launch_forward_any(a, raw_dtype, true, st, &g);
     if (rc != R2L_OK) return rc;
-    bn_finish_kernel<<<1, 32, 0, st>>>(a.chan_partials, g, (double)B * H * W, momentum, eps, running_mean,
+    bn_finish_kernel<<<1, 96, 0, st>>>(a.chan_partials, g, (double)B * H * W, momentum, eps, running_mean,
                                        running_var, saved_affine);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
@@ -405,7 +420,7 @@ int r2l_isp_bn_backward_prepare(const float* grad_out, const float* out, const f
     bn_backward_stats_kernel<<<dim3(kBnBwdBlocks, 3), 256, 0, st>>>(grad_out, out, B, H * W, partials);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
-    bn_backward_finish_kernel<<<1, 32, 0, st>>>(partials, saved_affine, (double)B * H * W, grad_tail);
+    bn_backward_finish_kernel<<<1, 96, 0, st>>>(partials, saved_affine, (double)B * H * W, grad_tail);
     e = cudaGetLastError();
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);
 }

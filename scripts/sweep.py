@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: ISP throughput sweep -- static (frozen, forward only) vs parametrized (forward + backward),
+256^2 .. 4096^2 synthetic Bayer frames, on one B200.  Prints one JSON line per point: Mpixel/s, achieved GB/s from
+the algorithmic bytes and the fraction of the measured HBM peak.  Working sets are kept above the L2
+(rotating buffer sets).  Kernel-level timing through the C ABI with CUDA events."""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from raw2logit_b200 import _lib, synthetic as syn  # noqa: E402
+from processing.pipeline_torch import ParametrizedProcessing  # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    mod = ParametrizedProcessing(syn.CAMERA_PRESETS["drone"], batch_norm_output=False).to(dev)
+    pt = [mod.black_level, mod.white_balance, mod.colour_correction, mod.gamma_correct, mod.debayer.weight,
+          mod.sharpening_filter.weight, mod.gaussian_blur.weight, mod.M_RGB_2_YUV, mod.M_YUV_2_RGB]
+    params = _lib.IspParams(*[t.data_ptr() for t in pt])
+    vp = ctypes.c_void_p
+    sp = vp(torch.cuda.current_stream().cuda_stream)
+    gpar = torch.empty(132, device=dev)
+    for size in (256, 512, 1024, 2048, 4096):
+        B = max(2, (64 * 256 * 256) // (size * size) * 4)          # 16.8 Mpx per buffer set (> L2 with outputs)
+        S = 3
+        pix = B * size * size
+        base = syn.smooth_scene(min(B, 4), size, size, "drone", seed=7).to(dev)
+        raws = [base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1)[:B].contiguous() for _ in range(S)]
+        outs = [torch.empty(B, 3, size, size, device=dev) for _ in range(S)]
+        gouts = [torch.full((B, 3, size, size), 1.0 / (3 * pix), device=dev) for _ in range(S)]
+        graws = [torch.empty(B, size, size, device=dev) for _ in range(S)]
+        nws = lib.r2l_isp_workspace_bytes(B, size, size)
+        ws = torch.empty(nws // 4, device=dev)
+
+        def fwd(s):
+            return lib.r2l_isp_forward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, size, size, ctypes.byref(params),
+                                       None, vp(outs[s].data_ptr()), sp)
+
+        def bwd(s, need_raw):
+            return lib.r2l_isp_backward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, size, size, ctypes.byref(params),
+                                        vp(gouts[s].data_ptr()), None, None,
+                                        vp(graws[s].data_ptr()) if need_raw else None, vp(gpar.data_ptr()),
+                                        vp(ws.data_ptr()), nws, sp)
+
+        def time_it(fn, n=12, warm=3):
+            for i in range(warm):
+                _lib.check(fn(i % S), "kernel")
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n):
+                fn(i % S)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        t_f = time_it(fwd)
+        t_b = time_it(lambda s: bwd(s, True))
+        t_bn = time_it(lambda s: bwd(s, False))
+        for mode, ms, bpp in (("static: forward only", t_f, 16), ("parametrized: forward + backward (raw grad)", t_f + t_b, 36),
+                              ("parametrized: forward + backward (no raw grad)", t_f + t_bn, 32)):
+            gbs = bpp * pix / (ms * 1e-3) / 1e9
+            print(json.dumps({"size": size, "batch": B, "mode": mode, "ms": round(ms, 4),
+                              "mpixel_per_s": round(pix / (ms * 1e-3) / 1e6, 1), "algorithmic_bytes_per_px": bpp,
+                              "achieved_gbs": round(gbs, 1), "frac_of_measured_hbm": round(gbs / peak, 4)}), flush=True)
+        del raws, outs, gouts, graws
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
