@@ -17,8 +17,12 @@
 //     shapes take the generic scalar kernel), so "inside the image" is one predicate per item;
 //   * threads are split by warp parity into the two CFA row phases, so the phase-bound weights (B2) and
 //     statistics (B7) stay in registers for every tile of the persistent CTA, with a uniform item count per warp;
-//   * statistics are accumulated next to the adjoint gathers (flipped form, see isp_bwd2.cuh) with run-level
-//     predicates only.
+//   * every correlation statistic is taken in its "flipped" form, a sum over the *stencil centre* q:
+//         dWg[t] = sum_q Y1pad(q) * gY2(q - t),   dWs[t] = sum_q Y0(q) * gY1(q - t),
+//         Q'[par(q)][k][t] = sum_q rawpad(q) * g_yuv[k](q - t)
+//     so the window the adjoint gather loads around q is reused for the statistic and only the centre value is read
+//     in addition; pad sites q outside the image belong to the nearest border tile; predicates are per run only.
+//     Q' is re-indexed to the p-based layout of kStatQ when the CTA writes its partial sums (finish_grad).
 // Shapes the fold pass cannot serve from one tile (a last tile row/column of <= 4 sites) go to the generic kernel.
 #pragma once
 #include <type_traits>

@@ -1,5 +1,4 @@
 // third-generation backward kernels, float32 raw
-#define R2L_EXPERIMENT_NT512 1
 #include "isp_bwd_tu.cuh"
 namespace r2l {
 int launch_backward3_f32(const BwdArgs& a, cudaStream_t st, int* grid_used) {

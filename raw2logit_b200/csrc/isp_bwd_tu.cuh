@@ -33,11 +33,6 @@ static int launch_backward3_impl(const BwdArgs& a, cudaStream_t st, int* grid_us
     if (!bwd3_shape_ok(a.H, a.W, Probe::TH, Probe::TW)) return kNotServed;
     if (!aligned(a.gout, 16) || !aligned(a.graw, 16) || !aligned(a.additive, 16)) return kNotServed;   // 128-bit rows
     const bool tail = a.gtail != nullptr;
-#ifdef R2L_EXPERIMENT_NT512
-    if (const char* nt = getenv("R2L_ISP_BWD_NT")) {                  // tuning experiment: 16 warps, 128 registers
-        if (nt[0] == '5' && a.graw && !tail) return launch_backward3_t<Bwd3Cfg<32, 64, 512, true, false>, RawT>(a, st, grid_used);
-    }
-#endif
     if (a.graw) return tail ? launch_backward3_t<Bwd3<true, true>, RawT>(a, st, grid_used)
                             : launch_backward3_t<Bwd3<true, false>, RawT>(a, st, grid_used);
     return tail ? launch_backward3_t<Bwd3<false, true>, RawT>(a, st, grid_used)

@@ -2,7 +2,6 @@
 #pragma once
 #include "isp_core.cuh"
 #include "isp_fwd2.cuh"
-#include "isp_bwd2.cuh"
 #include "isp_bwd3.cuh"
 #include "isp_fwd3.cuh"
 
@@ -11,8 +10,6 @@ using FwdDefault = FwdCfg<32, 64, 256>;          // v1 (scalar) -- kept for the 
 using Fwd2Default = Fwd2Cfg<32, 64, 256>;        // v2: image pairs, FFMA2, register micro-tiles (any shape)
 using Fwd3Default = Fwd3Cfg<32, 64, 256>;        // v3: border rules on the data, four barriers per tile (W % 4 == 0)
 using BwdNoRaw = BwdCfg<32, 64, 256, false>;     // v1 (scalar) -- emulation cross-check only
-using Bwd2NoRaw = Bwd2Cfg<32, 64, 256, false>;
-using Bwd2WithRaw = Bwd2Cfg<32, 64, 256, true>;
 using BwdWithRaw = BwdCfg<32, 64, 256, true>;
 // v3: branch-free padded-domain phases; <TH, TW, NT, GRAW, TAIL>
 template <bool GRAW, bool TAIL> using Bwd3 = Bwd3Cfg<32, 64, 256, GRAW, TAIL>;

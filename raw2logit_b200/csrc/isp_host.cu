@@ -5,6 +5,9 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC  (see _build.py)
 // No torch headers, no host-side state: every call validates its arguments, enqueues kernels on the caller's
 // stream and returns.
+#include <mutex>
+#include <vector>
+
 #include "isp_launch.h"
 
 namespace r2l {
@@ -258,6 +261,33 @@ __global__ void mosaic_backward_kernel(const float* gout, int B, int H, int W, i
 static thread_local int g_last_cuda_error = 0;
 
 int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return R2L_ERR_CUDA; }
+
+// resident CTAs of `kernel` on the current device (SM count x CTAs per SM), remembered per (kernel, device)
+int cached_ctas_per_device(const void* kernel, int threads, size_t smem, int* out) {
+    struct Entry { const void* kernel; int dev; int ctas; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (const Entry& en : cache)
+            if (en.kernel == kernel && en.dev == dev) { *out = en.ctas; return R2L_OK; }
+    }
+    int sms = 0, per_sm = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (e != cudaSuccess) return cuda_fail(e);
+    if (per_sm < 1) return R2L_ERR_BAD_ARGUMENT;
+    std::lock_guard<std::mutex> lock(mu);
+    cache.push_back({kernel, dev, sms * per_sm});
+    *out = sms * per_sm;
+    return R2L_OK;
+}
 
 static Params to_params(const r2l_isp_params* p) {
     Params q;

@@ -14,20 +14,14 @@ int cuda_fail(cudaError_t e);                      // records the error for r2l_
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-// persistent grid: one wave of resident CTAs (or fewer when the job is small)
+// persistent grid: one wave of resident CTAs (or fewer when the job is small).  The occupancy query and the
+// dynamic-shared-memory opt-in are done once per (kernel, device) and remembered (isp_host.cu).
+int cached_ctas_per_device(const void* kernel, int threads, size_t smem, int* out);   // fills *out, returns R2L_* code
 template <typename K>
 static int persistent_grid(K kernel, int threads, size_t smem, int n_tiles, int* grid_out) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return cuda_fail(e);
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return cuda_fail(e);
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
-    if (e != cudaSuccess) return cuda_fail(e);
-    if (per_sm < 1) return R2L_ERR_BAD_ARGUMENT;
-    int g = sms * per_sm;
+    int g = 0;
+    int rc = cached_ctas_per_device(reinterpret_cast<const void*>(kernel), threads, smem, &g);
+    if (rc != R2L_OK) return rc;
     if (g > n_tiles) g = n_tiles;
     if (g > kMaxCtas) g = kMaxCtas;
     *grid_out = g;

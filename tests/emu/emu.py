@@ -11,7 +11,6 @@ SRC = os.path.join(HERE, "isp_emu.cpp")
 LIB = os.path.join(HERE, "libisp_emu.so")
 DEPS = [SRC, os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_core.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_fwd2.cuh"),
-        os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd2.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd3.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_fwd3.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_config.h"), os.path.join(ROOT, "include", "r2l_isp.h")]

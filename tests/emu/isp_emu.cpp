@@ -66,13 +66,6 @@ static void run_backward(const BwdArgs& a, int n_cta, float* grads, int version)
         };
         if (a.gtail) go(Bwd3Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW, true>());
         else go(Bwd3Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW, false>());
-    } else {
-        using C2 = Bwd2Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW>;
-        const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, C2::TH, C2::TW);
-        std::vector<float> smem(C2::kSmemBytes / 4 + 4);
-        float* base = smem.data();
-        while (reinterpret_cast<uintptr_t>(base) % 16) ++base;
-        for (int cta = 0; cta < n_cta; ++cta) bwd2_cta<C2, RawT, false>(cta, n_cta, a, grid, base);
     }
     // finish (same arithmetic as isp_backward_finish_kernel)
     std::vector<float> tmem((sizeof(Tables) + 3) / 4);
