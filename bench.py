@@ -192,8 +192,8 @@ def run_ours(args):
 
     def step_backward(s):
         return lib.r2l_isp_backward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, H, W, ctypes.byref(params),
-                                    vp(gouts[s].data_ptr()), None, None, vp(graws[s].data_ptr()), vp(gpar.data_ptr()),
-                                    vp(wsb.data_ptr()), nws, sp)
+                                    vp(gouts[s].data_ptr()), None, None, vp(outs[s].data_ptr()), vp(graws[s].data_ptr()),
+                                    vp(gpar.data_ptr()), vp(wsb.data_ptr()), nws, sp)
 
     def barrier():
         if world > 1:

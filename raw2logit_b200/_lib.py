@@ -18,7 +18,7 @@ GRAD_LAYOUT = {
     "gauss_weight": (107, 25, (1, 1, 5, 5)),
 }
 F32, U16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = ("r2l_isp_abi_version", "r2l_isp_error_string", "r2l_isp_last_cuda_error", "r2l_isp_forward",
            "r2l_isp_workspace_bytes", "r2l_isp_forward_bn_train", "r2l_isp_bn_backward_prepare", "r2l_isp_backward",
@@ -62,7 +62,7 @@ def load():
     lib.r2l_isp_bn_backward_prepare.restype = ci
     lib.r2l_isp_bn_backward_prepare.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, sz, vp]
     lib.r2l_isp_backward.restype = ci
-    lib.r2l_isp_backward.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(IspParams), vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.r2l_isp_backward.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(IspParams), vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.r2l_isp_mosaic.restype = ci
     lib.r2l_isp_mosaic.argtypes = [vp, ci, cf, ci, ci, ci, vp, ci, ci, vp, vp]
     lib.r2l_isp_mosaic_backward.restype = ci

@@ -80,9 +80,10 @@ constexpr int kBwd3AccFloats = 2 + 25 + 9 + 54 + 6;
 
 // reflect-pad pre-images (isp_core.cuh: preimages1 / preimages2) are reused for the fold passes
 
-template <int TH_, int TW_, int NT_, bool GRAW_, bool TAIL_> struct Bwd3Cfg {
+template <int TH_, int TW_, int NT_, bool GRAW_, bool TAIL_, bool OUT_ = false> struct Bwd3Cfg {
     static constexpr int TH = TH_, TW = TW_, NT = NT_;
     static constexpr bool GRAW = GRAW_, TAIL = TAIL_;
+    static constexpr bool OUT = OUT_;     // the forward output is available: no Gaussian / colour-tail recompute
     static constexpr int G = TW / 4;
     static constexpr int PW = TW + 24;        // wide planes (raw, Y0, Y1): column index = gx - x0 + 12, run q = g + 3
     static constexpr int PN = TW + 16;        // narrow planes (F, gY1):    column index = gx - x0 + 8,  run q = g + 2
@@ -183,13 +184,15 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             // pulling its 128-byte lines into L2 now so those loads are L2 hits
             {
                 constexpr int LPR = TW * 4 / 128;                      // lines per owned row
-                const int rows = Cfg::FH, nl = rows * 6 * LPR;
+                constexpr int NP = Cfg::OUT ? 12 : 6;                  // planes: grad_out (and the forward output) x 3 x 2
+                const int rows = Cfg::FH, nl = rows * NP * LPR;
                 for (int i = tid; i < nl; i += NT) {
-                    const int l = i % LPR, pr = i / LPR, pk = pr % 6, rr = pr / 6;
+                    const int l = i % LPR, pr = i / LPR, pk = pr % NP, rr = pr / NP;
                     const int gy = ty0 - 4 + rr, gx = tx0 + l * 32;
-                    const int img = pk < 3 ? b0 : b1, k = pk < 3 ? pk : pk - 3;
+                    const int pk6 = pk % 6, img = pk6 < 3 ? b0 : b1, k = pk6 < 3 ? pk6 : pk6 - 3;
                     if (gy >= 0 && gy < H && gx < W) {
-                        const float* ptr = a.gout + ((size_t)img * 3 + k) * plane + (size_t)gy * W + gx;
+                        const float* base = pk < 6 ? a.gout : a.out;
+                        const float* ptr = base + ((size_t)img * 3 + k) * plane + (size_t)gy * W + gx;
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
                     }
                 }
@@ -199,7 +202,9 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             const RawT* stage = nullptr;
             constexpr int SX = 12, SP = PW;
 #endif
-            phase_deinterleave<PW, Cfg::RH, 8, 12, SP, SX - 12, NT, RawT, TMA>(tid, XR, stage, imgA, imgB, a.denom, ty0, tx0, H, W);
+            // with the forward output at hand only Y0 / Y1 around the tile are recomputed: raw rows -4..TH+3 suffice
+            phase_deinterleave<PW, Cfg::RH, 8, 12, SP, SX - 12, NT, RawT, TMA>(tid, XR, stage, imgA, imgB, a.denom, ty0, tx0, H, W,
+                                                                                Cfg::OUT ? 4 : 0, Cfg::OUT ? Cfg::RH - 4 : Cfg::RH);
         } }
         R2L_SYNC();
 #ifndef R2L_HOST_EMU
@@ -213,6 +218,46 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         }
 #endif
 
+        if (Cfg::OUT) {
+            // ---- B2 (forward output available): luma only, rows -3..TH+2 x runs -1..G; exact zero outside the image ----
+            { R2L_FOR_THREADS(NT) {
+                const int rp = (tid >> 5) & 1, slot = ((tid >> 6) << 5) | (tid & 31);
+                float wy[2][9];
+                {
+                    const f4* src = reinterpret_cast<const f4*>(T2->awy[rp]);
+                    float tmp[20];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) { const f4 v = src[q]; tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w; }
+#pragma unroll
+                    for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) wy[cp][t] = tmp[cp * 9 + t];
+                }
+                const float cb0 = T2->cbrow[rp][0], cb1 = T2->cbrow[rp][3];
+                // rows -3..TH+2 of this thread's CFA row phase: (TH+6)/2 rows x GG runs
+                const int r_first = -3 + ((-3 ^ rp) & 1);
+                for (int i = slot; i < ((TH + 6) / 2) * GG; i += HALF) {
+                    const int ri = i / GG, g = i - ri * GG - 1;
+                    const int ry = r_first + 2 * ri;
+                    f2 acc[4] = {mk2(-cb0, -cb0), mk2(-cb1, -cb1), mk2(-cb0, -cb0), mk2(-cb1, -cb1)};
+#pragma unroll
+                    for (int aa = 0; aa < 3; ++aa) {
+                        f2 in[6];
+                        ld6<PW>(XR, (ry + 7 + aa) * PW + 2 * (g + 3), in);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int bb = 0; bb < 3; ++bb) acc[j] = fma2s(in[j + bb], wy[j & 1][aa * 3 + bb], acc[j]);
+                    }
+                    const int gy = ty0 + ry, gx = tx0 + 4 * g;
+                    if (gy < 0 || gy >= H || gx < 0 || gx >= W) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[j] = mk2(0.f, 0.f);
+                    }
+                    st4<PW>(Y0, (ry + 7) * PW + 2 * (g + 3), acc[0], acc[1], acc[2], acc[3]);
+                }
+            } }
+        } else {
         // ---- B2: Y0 (exact zero outside the image) on rows -7..TH+6; U,V on the F region (rows -4..TH+3, runs -1..G)
         { R2L_FOR_THREADS(NT) {
             const int rp = (tid >> 5) & 1, slot = ((tid >> 6) << 5) | (tid & 31);
@@ -309,6 +354,7 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 st4<PW>(Y0, (ry + 7) * PW + 2 * (g + 3), acc[0], acc[1], acc[2], acc[3]);
             }
         } }
+        }
         R2L_SYNC();
 
         // ---- B3: Y1 = sharpen(Y0) on rows -6..TH+5, runs -2..G+1 (overwrites the raw window) ----------------------
@@ -320,9 +366,14 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             for (int t = 0; t < 9; ++t) ws[t] = T->Ws[t];
             const f2* __restrict__ Y0r = Y0;                            // B3 only reads Y0 and only writes Y1
             f2* __restrict__ Y1w = Y1;
+            // rows -6..TH+5 x runs -2..G+1; with the forward output only the statistic centres are needed:
+            // rows -2..TH+1 x runs -1..G (the pad ring matters at image borders only)
+            constexpr int kRows = Cfg::OUT ? TH + 4 : Cfg::Y1H, kRow0 = Cfg::OUT ? 4 : 0;
+            constexpr int kRuns = Cfg::OUT ? GG : G + 4, kRun0 = Cfg::OUT ? -1 : -2;
 #pragma unroll 2
-            for (int item = tid; item < Cfg::Y1H * (G + 4); item += NT) {
-                const int rr = item / (G + 4), g = item - rr * (G + 4) - 2;
+            for (int item = tid; item < kRows * kRuns; item += NT) {
+                const int rq = item / kRuns, g = item - rq * kRuns + kRun0;
+                const int rr = rq + kRow0;
                 const int gy = ty0 - 6 + rr, gx = tx0 + 4 * g;
                 if (gx < 0 || gx >= W) continue;
                 int sr = rr;                                           // Y0 rows sr .. sr+2 <-> image rows gy-1 .. gy+1
@@ -344,6 +395,83 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         } }
         R2L_SYNC();
 
+        if (Cfg::OUT) {
+            // ---- B4 (forward output y available): no Gaussian / colour-tail recompute.  o = y (or (y - shift)/scale -
+            // additive behind a tail); with lo = log2(o): e = cl^(1/g - 1) = 2^((1 - g) lo), log2(cl) = g lo, and the
+            // clamp passed iff o lies strictly between its two clipped values (exact compare without a tail, where o is
+            // bit-identical to the forward's; a 1e-4 / 1e-6 relative margin behind a tail, where o is recovered by an
+            // affine inverse).  All twelve 128-bit loads of an item are issued before the first use (the lines were
+            // prefetched into L2 during B1); deeper software pipelining across items / phases measured slower
+            // (load-queue throttling), profiles/r01_v4_summary.md.
+            { R2L_FOR_THREADS(NT) {
+                float m2g[9];
+                const float invg = T->invg, gam = T->gamma, one_m_g = 1.0f - T->gamma;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) m2g[t] = T->M2[t] * invg;
+                const float o_lo_exact = fast_exp2(invg * fast_log2(kClipLo));      // the forward's value of a low clip
+                const float o_lo = Cfg::TAIL ? o_lo_exact * (1.0f + 1e-4f) : o_lo_exact;
+                const float o_hi = Cfg::TAIL ? 1.0f - 1e-6f : 1.0f;
+                Bwd3Acc& acc = R2L_ACC(accs, tid);
+                for (int item = tid; item < Cfg::FH * GG; item += NT) {
+                    const int rr = item / GG, g = item - rr * GG - 1;
+                    const int r = rr - 4;
+                    const int gy = ty0 + r, gx = tx0 + 4 * g;
+                    const bool valid = gy >= 0 && gy < H && gx >= 0 && gx < W;
+                    const bool owned = r >= 0 && r < TH && g >= 0 && g < G;
+                    f2 gy2[4], gu[4], gv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { gy2[j] = mk2(0.f, 0.f); gu[j] = mk2(0.f, 0.f); gv[j] = mk2(0.f, 0.f); }
+                    if (valid) {
+                        const size_t pix = (size_t)gy * W + gx;
+                        f4 ga[3], gb[3], ya[3], yb[3], ad[3];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const size_t oa = ((size_t)b0 * 3 + k) * plane + pix, ob = ((size_t)b1 * 3 + k) * plane + pix;
+                            ga[k] = ld_stream4(a.gout + oa);
+                            ya[k] = ld_stream4(a.out + oa);
+                            gb[k] = ld_stream4(a.gout + ob);
+                            yb[k] = ld_stream4(a.out + ob);
+                            ad[k].x = ad[k].y = ad[k].z = ad[k].w = 0.f;
+                            if (Cfg::TAIL && a.additive) ad[k] = *reinterpret_cast<const f4*>(a.additive + (size_t)k * plane + pix);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const float gak[4] = {ga[k].x, ga[k].y, ga[k].z, ga[k].w}, gbk[4] = {gb[k].x, gb[k].y, gb[k].z, gb[k].w};
+                            const float yak[4] = {ya[k].x, ya[k].y, ya[k].z, ya[k].w}, ybk[4] = {yb[k].x, yb[k].y, yb[k].z, yb[k].w};
+                            const float adk[4] = {ad[k].x, ad[k].y, ad[k].z, ad[k].w};
+                            float t_gs = 1.f, t_c1 = 0.f, t_c2 = 0.f, t_isc = 1.f, t_osh = 0.f;
+                            if (Cfg::TAIL) {
+                                t_gs = a.gtail[k]; t_c1 = a.gtail[3 + k]; t_c2 = a.gtail[6 + k];
+                                t_isc = 1.0f / a.gtail[9 + k]; t_osh = -a.gtail[12 + k] * t_isc;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float Ga = gak[j], Gb = dup ? 0.f : gbk[j];
+                                f2 o = mk2(yak[j], ybk[j]);
+                                if (Cfg::TAIL) {
+                                    Ga = t_gs * (Ga - t_c1 - t_c2 * o.x);
+                                    Gb = dup ? 0.f : t_gs * (Gb - t_c1 - t_c2 * o.y);
+                                    o = mk2(fmaf_(o.x, t_isc, t_osh) - adk[j], fmaf_(o.y, t_isc, t_osh) - adk[j]);
+                                }
+                                const f2 lo = mk2(fast_log2(o.x), fast_log2(o.y));
+                                const f2 ex = mul2s(lo, one_m_g);
+                                const f2 e = mk2(fast_exp2(ex.x), fast_exp2(ex.y));
+                                if (owned) acc.sg = fma2vv(mk2(Ga * o.x, Gb * o.y), mul2s(lo, gam), acc.sg);
+                                const f2 gr = mk2((o.x > o_lo && o.x < o_hi) ? Ga * e.x : 0.f,
+                                                  (o.y > o_lo && o.y < o_hi) ? Gb * e.y : 0.f);
+                                gy2[j] = fma2s(gr, m2g[k * 3 + 0], gy2[j]);
+                                gu[j] = fma2s(gr, m2g[k * 3 + 1], gu[j]);
+                                gv[j] = fma2s(gr, m2g[k * 3 + 2], gv[j]);
+                            }
+                        }
+                    }
+                    st4<PN>(PG, (r + 4) * PN + 2 * (g + 2), gy2[0], gy2[1], gy2[2], gy2[3]);
+                    st4<PN>(PU, (r + 4) * PN + 2 * (g + 2), gu[0], gu[1], gu[2], gu[3]);
+                    st4<PN>(PV, (r + 4) * PN + 2 * (g + 2), gv[0], gv[1], gv[2], gv[3]);
+                }
+            } }
+            R2L_SYNC();
+        } else {
         // ---- B4: forward tail recomputed on the F region; grad_out pulled back to (gY2, gU, gV); gamma statistic ----
         // With cl = clip(rgb), l2 = log2(cl), e = cl^(1/g - 1) = 2^((1/g - 1) l2):  o = cl e,  dL/drgb = pass G e / g,
         // and the gamma statistic sum G o l2 = sum (G e)(cl l2) -- two MUFU per value.
@@ -429,6 +557,7 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             }
         } }
         R2L_SYNC();
+        }
 
         // ---- B5: gY1 on the padded domain = corr^T(gY2, Wg), rows -2..TH+1, runs -1..G; flipped Wg statistic --------
         { R2L_FOR_THREADS(NT) {

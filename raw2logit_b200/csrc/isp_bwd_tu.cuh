@@ -33,6 +33,12 @@ static int launch_backward3_impl(const BwdArgs& a, cudaStream_t st, int* grid_us
     if (!bwd3_shape_ok(a.H, a.W, Probe::TH, Probe::TW)) return kNotServed;
     if (!aligned(a.gout, 16) || !aligned(a.graw, 16) || !aligned(a.additive, 16)) return kNotServed;   // 128-bit rows
     const bool tail = a.gtail != nullptr;
+    if (a.out && aligned(a.out, 16)) {                  // forward output at hand: no Gaussian / colour-tail recompute
+        if (a.graw) return tail ? launch_backward3_t<Bwd3<true, true, true>, RawT>(a, st, grid_used)
+                                : launch_backward3_t<Bwd3<true, false, true>, RawT>(a, st, grid_used);
+        return tail ? launch_backward3_t<Bwd3<false, true, true>, RawT>(a, st, grid_used)
+                    : launch_backward3_t<Bwd3<false, false, true>, RawT>(a, st, grid_used);
+    }
     if (a.graw) return tail ? launch_backward3_t<Bwd3<true, true>, RawT>(a, st, grid_used)
                             : launch_backward3_t<Bwd3<true, false>, RawT>(a, st, grid_used);
     return tail ? launch_backward3_t<Bwd3<false, true>, RawT>(a, st, grid_used)

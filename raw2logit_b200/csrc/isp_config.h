@@ -11,7 +11,7 @@ using Fwd2Default = Fwd2Cfg<32, 64, 256>;        // v2: image pairs, FFMA2, regi
 using Fwd3Default = Fwd3Cfg<32, 64, 256>;        // v3: border rules on the data, four barriers per tile (W % 4 == 0)
 using BwdNoRaw = BwdCfg<32, 64, 256, false>;     // v1 (scalar) -- emulation cross-check only
 using BwdWithRaw = BwdCfg<32, 64, 256, true>;
-// v3: branch-free padded-domain phases; <TH, TW, NT, GRAW, TAIL>
-template <bool GRAW, bool TAIL> using Bwd3 = Bwd3Cfg<32, 64, 256, GRAW, TAIL>;
+// v3: branch-free padded-domain phases; <TH, TW, NT, GRAW, TAIL, OUT (forward output available)>
+template <bool GRAW, bool TAIL, bool OUT = false> using Bwd3 = Bwd3Cfg<32, 64, 256, GRAW, TAIL, OUT>;
 constexpr int kMaxCtas = 2048;          // upper bound on persistent CTAs == rows of the statistics workspace
 }  // namespace r2l

@@ -461,6 +461,8 @@ struct BwdArgs {
     const float* additive; // (3,H,W) or null, only read when gtail is given
     float* graw;           // (B,H,W) or null
     float* partials;       // [n_cta][kStatPitch]
+    const float* out;      // null, or the forward's output (B,3,H,W): lets the vectorised backward skip the Gaussian /
+                           // colour-tail recompute (the generic kernel ignores it)
 };
 
 // gather of the transposed 5x5 at a (possibly padded) site q': sum_ij Wg[ij] * gY2(q' - (i-2, j-2)), in-image only

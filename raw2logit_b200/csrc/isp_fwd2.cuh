@@ -74,11 +74,11 @@ template <int P> R2L_HD void ld4(const f2* pl, int eb, f2 v[4]) {
 // The outermost run on each side (beyond the halo any consumer reads) is skipped.
 template <int P, int RH, int ROFF, int COFF, int SP, int SOFF, int NT, typename RawT, bool TMA>
 R2L_HD void phase_deinterleave(int tid, f2* __restrict__ XR, const RawT* __restrict__ stage, const RawT* imgA,
-                               const RawT* imgB, float denom, int ty0, int tx0, int H, int W) {
+                               const RawT* imgB, float denom, int ty0, int tx0, int H, int W, int ly0 = 0, int ly1 = RH) {
     constexpr int Q = P / 4, QI = Q - 2;
 #pragma unroll 2
-    for (int i = tid; i < RH * QI; i += NT) {
-        const int ly = i / QI, lq = i - ly * QI + 1;
+    for (int i = tid; i < (ly1 - ly0) * QI; i += NT) {                 // plane rows ly0 .. ly1-1
+        const int lr = i / QI, lq = i - lr * QI + 1, ly = ly0 + lr;
         const int gy = ty0 - ROFF + ly, gx = tx0 - COFF + 4 * lq;
         if ((unsigned)gx >= (unsigned)W) continue;
         int sy = gy;

@@ -457,7 +457,7 @@ int r2l_isp_bn_backward_prepare(const float* grad_out, const float* out, const f
 
 int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
                      const r2l_isp_params* params, const float* grad_out, const float* grad_tail,
-                     const float* additive, float* grad_raw, float* grad_params, void* workspace,
+                     const float* additive, const float* out, float* grad_raw, float* grad_params, void* workspace,
                      size_t workspace_bytes, void* stream) {
     int rc = check_common(raw, raw_dtype, B, H, W, params);
     if (rc != R2L_OK) return rc;
@@ -473,6 +473,8 @@ int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int 
     BwdArgs a;
     a.raw = raw; a.denom = raw_denominator; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.gout = grad_out; a.gtail = grad_tail; a.additive = additive; a.graw = grad_raw; a.partials = static_cast<float*>(workspace);
+    a.out = out;
+    if (out && additive && !grad_tail) return R2L_ERR_BAD_ARGUMENT;   // an additive tail needs grad_tail to invert it
     return launch_backward_any(a, raw_dtype, grad_params, st);
 }
 

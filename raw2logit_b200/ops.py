@@ -8,6 +8,7 @@ Replaces the 79-node autograd graph the reference records per call (pipeline_tor
 one forward kernel launch and one backward launch (+ a 1-CTA finish kernel for the 132 parameter gradients).
 """
 import ctypes
+import os
 
 import torch
 
@@ -23,7 +24,7 @@ _library.define(f"forward_bn_train(Tensor raw, {_PARAMS_SCHEMA}, Tensor? additiv
                 "Tensor(b!)? running_var, float momentum, float eps, float raw_denominator) -> (Tensor, Tensor)")
 _library.define("bn_backward_prepare(Tensor grad_out, Tensor out, Tensor saved_affine) -> Tensor")
 _library.define(f"backward(Tensor raw, {_PARAMS_SCHEMA}, Tensor grad_out, Tensor? grad_tail, Tensor? additive, "
-                "bool need_raw_grad, float raw_denominator) -> (Tensor, Tensor)")
+                "Tensor? out, bool need_raw_grad, float raw_denominator) -> (Tensor, Tensor)")
 _library.define("mosaic(Tensor raw, Tensor? black_level, bool reduce_size, int out_channels, float raw_denominator) -> Tensor")
 _library.define("mosaic_backward(Tensor grad_out, int H, int W, bool reduce_size, int out_channels) -> Tensor")
 _library.define("batch_sum(Tensor x, Tensor? scale) -> Tensor")
@@ -129,7 +130,7 @@ def _bn_backward_prepare_cuda(grad_out, out, saved_affine):
     return tail
 
 
-def _backward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, grad_tail, additive, need_raw_grad,
+def _backward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, grad_tail, additive, out, need_raw_grad,
                    raw_denominator):
     lib = _lib.load()
     b, h, w = _check_shape(raw)
@@ -139,12 +140,13 @@ def _backward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, grad_t
         g = _f32c(grad_out, b * 3 * h * w, "grad_out")
         gs = None if grad_tail is None else _f32c(grad_tail, 15, "grad_tail")
         add = None if additive is None else _f32c(additive, 3 * h * w, "additive")
+        y = None if out is None else _f32c(out, b * 3 * h * w, "out")
         graw = torch.empty((b, h, w), dtype=torch.float32, device=raw.device) if need_raw_grad else None
         gpar = torch.empty(_lib.NUM_PARAM_GRADS, dtype=torch.float32, device=raw.device)
         nbytes = lib.r2l_isp_workspace_bytes(b, h, w)
         ws_buf = torch.empty(nbytes // 4, dtype=torch.float32, device=raw.device)
         rc = lib.r2l_isp_backward(_ptr(raw), code, raw_denominator, b, h, w, ctypes.byref(params), _ptr(g), _ptr(gs),
-                                  _ptr(add), _ptr(graw), _ptr(gpar), _ptr(ws_buf), nbytes, _stream())
+                                  _ptr(add), _ptr(y), _ptr(graw), _ptr(gpar), _ptr(ws_buf), nbytes, _stream())
     _lib.check(rc, "r2l_isp_backward")
     if graw is None:
         graw = torch.empty(0, dtype=torch.float32, device=raw.device)
@@ -210,10 +212,12 @@ _ops = getattr(torch.ops, _NS)
 class FusedISP(torch.autograd.Function):
     """raw (B,H,W) + 7 parameter tensors + 2 buffers [+ additive] [+ BatchNorm tail] -> (B,3,H,W).
 
-    Saves only ``raw`` and the (tiny) parameters (plus the output when the train-mode BatchNorm tail is on, whose
-    backward needs it); the backward kernel recomputes the forward per tile.  Gradients are returned for raw (if
-    needed), the 7 parameter tensors and the additive layer; the colour-space buffers and the BatchNorm statistics
-    get none, as in the reference.
+    Saves ``raw``, the (tiny) parameters and the output tensor (which the consumer of the output keeps alive
+    anyway): the backward kernel recomputes Y0 / Y1 per tile from ``raw`` and reads the clip mask and the gamma
+    derivative off the saved output instead of recomputing the Gaussian and the colour tail (``R2L_ISP_RECOMPUTE=1``
+    makes it recompute everything from ``raw``).  Gradients are returned for raw (if needed), the 7 parameter
+    tensors and the additive layer; the colour-space buffers and the BatchNorm statistics get none, as in the
+    reference.
 
     bn_mode: 0 = no tail, 1 = eval (affine from running statistics), 2 = train (batch statistics, running
     statistics updated in place by the kernel).
@@ -223,19 +227,18 @@ class FusedISP(torch.autograd.Function):
     def forward(ctx, raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, bn_mode, running_mean, running_var,
                 momentum, eps, raw_denominator):
         params = (bl, wb, ccm, gamma, wd, ws, wg, m1, m2)
-        saved_affine, out_saved = None, None
+        saved_affine = None
         if bn_mode == 2:
             out, saved_affine = _ops.forward_bn_train(raw, *params, additive, running_mean, running_var,
                                                       momentum, eps, raw_denominator)
             ctx.mark_non_differentiable(saved_affine)
-            out_saved = out
         elif bn_mode == 1:
             scale = torch.rsqrt(running_var + eps)
             saved_affine = torch.cat([scale, -running_mean * scale])
             out = _ops.forward(raw, *params, additive, saved_affine, raw_denominator)
         else:
             out = _ops.forward(raw, *params, additive, None, raw_denominator)
-        ctx.save_for_backward(raw, *params, additive, saved_affine, out_saved)
+        ctx.save_for_backward(raw, *params, additive, saved_affine, out)
         ctx.bn_mode = bn_mode
         ctx.raw_denominator = raw_denominator
         return out
@@ -248,14 +251,20 @@ class FusedISP(torch.autograd.Function):
         need_raw = ctx.needs_input_grad[0]
         grad_out = grad_out.contiguous()
         grads = [None] * 17
+        # 15-float description of the tail the forward applied: {gs, c1, c2, ysc, ysh} x 3 channels (r2l_isp.h)
         tail = None
         if ctx.bn_mode == 2:
             tail = _ops.bn_backward_prepare(grad_out, out_saved, saved_affine)
         elif ctx.bn_mode == 1:
-            tail = torch.cat([saved_affine[:3], saved_affine.new_zeros(12)])
+            zeros = saved_affine.new_zeros(6)
+            tail = torch.cat([saved_affine[:3], zeros, saved_affine])        # gs = ysc = scale, c1 = c2 = 0, ysh = shift
+        elif additive is not None:
+            one, zero = grad_out.new_ones(3), grad_out.new_zeros(3)
+            tail = torch.cat([one, zero, zero, one, zero])                   # identity affine around the additive layer
+        use_out = os.environ.get("R2L_ISP_RECOMPUTE", "0") != "1"
         if need_raw or any(ctx.needs_input_grad[1:8]):
-            graw, gpar = _ops.backward(raw, *params, grad_out, tail, additive if ctx.bn_mode == 2 else None,
-                                       need_raw, ctx.raw_denominator)
+            graw, gpar = _ops.backward(raw, *params, grad_out, tail, additive if tail is not None else None,
+                                       out_saved if use_out else None, need_raw, ctx.raw_denominator)
             if need_raw:
                 grads[0] = graw if raw.dtype == torch.float32 else graw.to(raw.dtype)
             for slot, name in enumerate(_lib.PARAM_FIELDS[:7], start=1):

@@ -46,7 +46,7 @@ def main():
 
         def bwd(s, need_raw):
             return lib.r2l_isp_backward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, size, size, ctypes.byref(params),
-                                        vp(gouts[s].data_ptr()), None, None,
+                                        vp(gouts[s].data_ptr()), None, None, vp(outs[s].data_ptr()),
                                         vp(graws[s].data_ptr()) if need_raw else None, vp(gpar.data_ptr()),
                                         vp(ws.data_ptr()), nws, sp)
 

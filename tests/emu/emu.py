@@ -76,7 +76,7 @@ def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0, vers
 
 
 def backward(raw, state, grad_out, need_raw_grad=True, n_cta=3, denom=65535.0, grad_tail=None, additive=None,
-             version=3):
+             version=3, out=None):
     raw = np.ascontiguousarray(raw)
     dtype = 1 if raw.dtype == np.uint16 else 0
     if dtype == 0:
@@ -88,12 +88,14 @@ def backward(raw, state, grad_out, need_raw_grad=True, n_cta=3, denom=65535.0, g
     gpar = np.full(132, np.nan, dtype=np.float32)
     gs = None if grad_tail is None else _f32(grad_tail)
     add = None if additive is None else _f32(additive)
+    outc = None if out is None else _f32(out)
     rc = lib().emu_isp_backward(ctypes.c_void_p(raw.ctypes.data), dtype, ctypes.c_float(denom), b, h, w,
                                 ctypes.byref(p), ctypes.c_void_p(g.ctypes.data),
                                 None if gs is None else ctypes.c_void_p(gs.ctypes.data),
                                 None if add is None else ctypes.c_void_p(add.ctypes.data),
                                 None if graw is None else ctypes.c_void_p(graw.ctypes.data),
-                                ctypes.c_void_p(gpar.ctypes.data), n_cta, version)
+                                ctypes.c_void_p(gpar.ctypes.data), n_cta, version,
+                                None if outc is None else ctypes.c_void_p(outc.ctypes.data))
     assert rc == 0, rc
     grads = {k: gpar[a:b_] for k, (a, b_) in GRAD_SLICES.items()}
     if graw is not None:

@@ -64,7 +64,10 @@ static void run_backward(const BwdArgs& a, int n_cta, float* grads, int version)
             while (reinterpret_cast<uintptr_t>(base) % 16) ++base;
             for (int cta = 0; cta < n_cta; ++cta) bwd3_cta<C3, RawT, false>(cta, n_cta, a, grid, base);
         };
-        if (a.gtail) go(Bwd3Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW, true>());
+        if (a.out) {
+            if (a.gtail) go(Bwd3Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW, true, true>());
+            else go(Bwd3Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW, false, true>());
+        } else if (a.gtail) go(Bwd3Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW, true>());
         else go(Bwd3Cfg<Cfg::TH, Cfg::TW, Cfg::NT, Cfg::GRAW, false>());
     }
     // finish (same arithmetic as isp_backward_finish_kernel)
@@ -131,12 +134,13 @@ int emu_isp_forward(const void* raw, int raw_dtype, float denom, int B, int H, i
 
 int emu_isp_backward(const void* raw, int raw_dtype, float denom, int B, int H, int W, const r2l_isp_params* params,
                      const float* grad_out, const float* grad_tail, const float* additive, float* grad_raw,
-                     float* grad_params, int n_cta, int version) {
+                     float* grad_params, int n_cta, int version, const float* out) {
     if (H < 3 || W < 3) return R2L_ERR_BAD_SHAPE;
     std::vector<float> partials((size_t)n_cta * kStatPitch, 0.f);
     BwdArgs a;
     a.raw = raw; a.denom = denom; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.gout = grad_out; a.gtail = grad_tail; a.additive = additive; a.graw = grad_raw; a.partials = partials.data();
+    a.out = out;
     if (grad_raw) {
         if (raw_dtype == R2L_F32) run_backward<BwdWithRaw, float>(a, n_cta, grad_params, version);
         else run_backward<BwdWithRaw, uint16_t>(a, n_cta, grad_params, version);

@@ -323,3 +323,35 @@ def test_track_stages_mode_matches_reference_stages_and_stage_gradients(cot):
     # without a raw gradient the stages are populated but nothing is retained (pipeline_torch.py:219-221)
     out2 = mod(c.raw.cuda())
     assert len(mod.stages) == 6 and out2.shape == out.shape
+
+
+@pytest.mark.parametrize("shape", [(5, 256, 256), (2, 96, 200), (3, 72, 136)])
+@pytest.mark.parametrize("tail", ["none", "bn_train", "bn_eval", "additive"])
+def test_backward_from_saved_output_agrees_with_full_recompute(shape, tail):
+    """Default backward (clip mask / gamma derivative read off the saved forward output) against the variant that
+    recomputes everything from raw (R2L_ISP_RECOMPUTE=1), with and without the BatchNorm / additive tails."""
+    import os
+    from processing.pipeline_torch import ParametrizedProcessing
+    state = syn.perturbed_state(isp_oracle.default_state(syn.CAMERA_PRESETS["drone"]))
+    raw = syn.smooth_scene(*shape, "drone", seed=41).cuda()
+    g = isp_oracle.cotangent((shape[0], 3, shape[1], shape[2]), "ramp").cuda()
+    res = []
+    for mode in ("0", "1"):
+        os.environ["R2L_ISP_RECOMPUTE"] = mode
+        try:
+            bn = tail.startswith("bn")
+            mod = ParametrizedProcessing(syn.CAMERA_PRESETS["drone"], batch_norm_output=bn)
+            mod.load_state_dict(state, strict=not bn)
+            if tail == "additive":
+                torch.manual_seed(3)
+                mod.additive_layer = torch.nn.Parameter(0.01 * torch.randn(1, 3, shape[1], shape[2]))
+            mod = mod.cuda().train(tail != "bn_eval")
+            x = raw.clone().requires_grad_(True)
+            mod(x).backward(g)
+            flat = torch.cat([p.grad.flatten() for p in mod.parameters()]).cpu()
+            res.append((flat, x.grad.cpu()))
+        finally:
+            os.environ["R2L_ISP_RECOMPUTE"] = "0"
+    (pa, ra), (pb, rb) = res
+    assert maxabs(pa, pb) <= 2e-5 * max(1.0, pb.abs().max().item()), (shape, tail, maxabs(pa, pb))
+    assert maxabs(ra, rb) <= 2e-5 * max(1.0, rb.abs().max().item()), (shape, tail, maxabs(ra, rb))
