@@ -720,8 +720,12 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         } }
         R2L_SYNC();
 
-        // ---- B7: Q' / P statistics and the padded g_raw from the (gY0, gU, gV) windows ----------------------------------
-        // domain: owned rectangle, plus the reflect-1 pad ring where the tile ends exactly at the image border
+        // ---- B7: Q' / P statistics and g_raw from the (gY0, gU, gV) windows -------------------------------------------
+        // The reflect-1 padding of the mosaic (pipeline_torch.py:233) folds the pad ring onto rows 1 / H-2 and columns
+        // 1 / W-2.  A pad site's contribution only involves gradient values the folded-onto site already holds in its
+        // window (pad row -1 reaches row 0 only, through the tap row a = 0; pad column -1 reaches column 0 through
+        // b = 0; ...) and its raw value is the folded-onto site's own, so the fold is a few extra products inside
+        // the items of those rows / columns: no pad items, no staging, no second pass, stores go straight to global.
         { R2L_FOR_THREADS(NT) {
             const int rp = (tid >> 5) & 1, slot = ((tid >> 6) << 5) | (tid & 31);
             Bwd3Acc& acc = R2L_ACC(accs, tid);
@@ -734,42 +738,24 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
                         for (int t = 0; t < 9; ++t) awq[cp][k][t] = T->AWq[2 * rp + cp][k][t];
             }
-            // items of this thread's row phase: the owned rows first (TH/2 x G, the same count for every thread), then
-            // the pad ring: row -1 (phase 1) / row TH (phase 0) and the runs -1 / G beside the owned rows
-            const int x_bot = ty0 + TH == H, x_rgt = tx0 + TW == W;
-            const int g_lo = e_lft ? -1 : 0, nruns = G + e_lft + x_rgt;
-            const int n_tb = (rp ? e_top : x_bot) ? nruns : 0;
-            const int n_ring = n_tb + (e_lft + x_rgt) * (TH / 2);
-            for (int i = slot; i < (TH / 2) * G + n_ring; i += HALF) {
-                int r, g;
-                if (i < (TH / 2) * G) {
-                    const int ri = i / G;
-                    r = rp + 2 * ri; g = i - ri * G;
-                } else {
-                    int h = i - (TH / 2) * G;
-                    if (h < n_tb) { r = rp ? -1 : TH; g = g_lo + h; }
-                    else {
-                        h -= n_tb;
-                        const int side = h / (TH / 2);
-                        r = rp + 2 * (h - side * (TH / 2));
-                        g = (side == 0 && e_lft) ? -1 : G;
-                    }
-                }
+            // owned rows of this thread's row phase: TH/2 rows x G runs, the same count for every thread
+            for (int i = slot; i < (TH / 2) * G; i += HALF) {
+                const int ri = i / G, g = i - ri * G;
+                const int r = rp + 2 * ri;
                 const int qy = ty0 + r, qx = tx0 + 4 * g;
-                // raw centres of the 4 sites (the reflected mosaic on pad sites)
+                if (qy >= H || qx >= W) continue;                       // partial tiles: nothing there (all gradients zero)
+                const bool f_top = qy == 1, f_bot = qy == H - 2, f_lft = qx == 0, f_rgt = qx + 4 == W;
+                // raw centres of the 4 sites
                 f2 c[4];
-                if (TMA && sizeof(RawT) == 4 && qy >= 0 && qy < H && qx >= 0 && qx < W) {
+                if (TMA && sizeof(RawT) == 4) {
                     const f4 xa = *reinterpret_cast<const f4*>(reinterpret_cast<const float*>(imgA) + (size_t)qy * W + qx);
                     const f4 xb = *reinterpret_cast<const f4*>(reinterpret_cast<const float*>(imgB) + (size_t)qy * W + qx);
                     c[0] = mk2(xa.x, xb.x); c[1] = mk2(xa.y, xb.y); c[2] = mk2(xa.z, xb.z); c[3] = mk2(xa.w, xb.w);
                 } else {
-                    const int sy = mirror_clamped(qy, H);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int sx = mirror_clamped(qx + j, W);
-                        c[j] = mk2(RawLoad<RawT>::get(imgA + (size_t)sy * W + sx, a.denom),
-                                   RawLoad<RawT>::get(imgB + (size_t)sy * W + sx, a.denom));
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        c[j] = mk2(RawLoad<RawT>::get(imgA + (size_t)qy * W + qx + j, a.denom),
+                                   RawLoad<RawT>::get(imgB + (size_t)qy * W + qx + j, a.denom));
                 }
                 f2 graw[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
 #pragma unroll
@@ -777,7 +763,7 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     f2* pl = k == 0 ? PG : (k == 1 ? PU : PV);
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
-                        f2 row[6];                                      // g_yuv[k] row q.y - 1 + d
+                        f2 row[6];                                      // g_yuv[k] row q.y - 1 + d, columns q.x - 1 .. q.x + 4
                         ld6<PN>(pl, (r + 3 + d) * PN + 2 * (g + 2), row);
                         const int aa = 2 - d;
 #pragma unroll
@@ -792,63 +778,54 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
                             for (int j = 0; j < 4; ++j) acc.p[j & 1][k] += row[j + 1].x + row[j + 1].y;
                         }
+                        // ---- folded pad contributions (uniform per item; rows 1 / H-2 and the first / last run only) ----
+                        // pad row above (d == 0 is image row 0, reached through tap row 0) / below (d == 2, tap row 2)
+                        if ((f_top && d == 0) || (f_bot && d == 2)) {
+                            const int ap = d;                            // tap row of the pad site: 0 above, 2 below
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int bb = 0; bb < 3; ++bb) {
+                                    const f2 t = row[j + 2 - bb];
+                                    acc.q[j & 1][k][ap * 3 + bb] = fmaf_(c[j].x, t.x, fmaf_(c[j].y, t.y, acc.q[j & 1][k][ap * 3 + bb]));
+                                    if (Cfg::GRAW) graw[j] = fma2s(t, awq[j & 1][k][ap * 3 + bb], graw[j]);
+                                }
+                        }
+                        // pad column left of the image folds onto site j = 1 (column 1) through b = 0, value at column 0
+                        if (f_lft) {
+                            const f2 t = row[1];
+                            acc.q[1][k][aa * 3 + 0] = fmaf_(c[1].x, t.x, fmaf_(c[1].y, t.y, acc.q[1][k][aa * 3 + 0]));
+                            if (Cfg::GRAW) graw[1] = fma2s(t, awq[1][k][aa * 3 + 0], graw[1]);
+                            if ((f_top && d == 0) || (f_bot && d == 2)) {            // corner pad
+                                acc.q[1][k][d * 3 + 0] = fmaf_(c[1].x, t.x, fmaf_(c[1].y, t.y, acc.q[1][k][d * 3 + 0]));
+                                if (Cfg::GRAW) graw[1] = fma2s(t, awq[1][k][d * 3 + 0], graw[1]);
+                            }
+                        }
+                        // pad column right of the image folds onto site j = 2 (column W-2) through b = 2, value at column W-1
+                        if (f_rgt) {
+                            const f2 t = row[4];
+                            acc.q[0][k][aa * 3 + 2] = fmaf_(c[2].x, t.x, fmaf_(c[2].y, t.y, acc.q[0][k][aa * 3 + 2]));
+                            if (Cfg::GRAW) graw[2] = fma2s(t, awq[0][k][aa * 3 + 2], graw[2]);
+                            if ((f_top && d == 0) || (f_bot && d == 2)) {            // corner pad
+                                acc.q[0][k][d * 3 + 2] = fmaf_(c[2].x, t.x, fmaf_(c[2].y, t.y, acc.q[0][k][d * 3 + 2]));
+                                if (Cfg::GRAW) graw[2] = fma2s(t, awq[0][k][d * 3 + 2], graw[2]);
+                            }
+                        }
                     }
                 }
                 if (Cfg::GRAW) {
-                    // runs that receive folded pad contributions (rows 1 / H-2, first / last run of the image) and the
-                    // pad ring itself go through shared memory; everything else goes straight to global
-                    const bool ring = r < 0 || r >= TH || g < 0 || g >= G;
-                    const bool special = qy == 1 || qy == H - 2 || qx == 0 || qx + 4 == W;
-                    if (border && (ring || special || qy >= H || qx >= W)) {
-                        st4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), graw[0], graw[1], graw[2], graw[3]);
-                    } else {
-                        float* pa = a.graw + (size_t)b0 * plane + (size_t)qy * W + qx;
-                        f4 va; va.x = graw[0].x; va.y = graw[1].x; va.z = graw[2].x; va.w = graw[3].x;
-                        *reinterpret_cast<f4*>(pa) = va;
-                        if (!dup) {
-                            float* pb = a.graw + (size_t)b1 * plane + (size_t)qy * W + qx;
-                            f4 vb; vb.x = graw[0].y; vb.y = graw[1].y; vb.z = graw[2].y; vb.w = graw[3].y;
-                            *reinterpret_cast<f4*>(pb) = vb;
-                        }
+                    float* pa = a.graw + (size_t)b0 * plane + (size_t)qy * W + qx;
+                    f4 va; va.x = graw[0].x; va.y = graw[1].x; va.z = graw[2].x; va.w = graw[3].x;
+                    *reinterpret_cast<f4*>(pa) = va;
+                    if (!dup) {
+                        float* pb = a.graw + (size_t)b1 * plane + (size_t)qy * W + qx;
+                        f4 vb; vb.x = graw[0].y; vb.y = graw[1].y; vb.z = graw[2].y; vb.w = graw[3].y;
+                        *reinterpret_cast<f4*>(pb) = vb;
                     }
                 }
             }
         } }
-        R2L_SYNC();
-        if (Cfg::GRAW && border) {
-            // owned sites -> global, folding the reflect-1 pad ring onto rows/columns 1 and n-2 on the way
-            { R2L_FOR_THREADS(NT) {
-                for (int item = tid; item < TH * G; item += NT) {
-                    const int r = item / G, g = item - r * G;
-                    const int qy = ty0 + r, qx = tx0 + 4 * g;
-                    if (qy >= H || qx >= W) continue;
-                    if (!(qy == 1 || qy == H - 2 || qx == 0 || qx + 4 == W)) continue;     // stored by B7 already
-                    f2 v[4];
-                    ld4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), v);
-                    {
-                        for (int j = 0; j < 4; ++j) {
-                            int ys[3], xs[3];
-                            const int ny = preimages1(qy, H, ys), nx = preimages1(qx + j, W, xs);
-                            if (ny * nx == 1) continue;
-                            f2 s = mk2(0.f, 0.f);
-                            for (int iy = 0; iy < ny; ++iy)
-                                for (int ix = 0; ix < nx; ++ix)
-                                    s = add2v(s, site3<PN>(GY1, ys[iy] - (ty0 - 2), xs[ix] - (tx0 - 8)));
-                            v[j] = s;
-                        }
-                    }
-                    float* pa = a.graw + (size_t)b0 * plane + (size_t)qy * W + qx;
-                    f4 va; va.x = v[0].x; va.y = v[1].x; va.z = v[2].x; va.w = v[3].x;
-                    *reinterpret_cast<f4*>(pa) = va;
-                    if (!dup) {
-                        float* pb = a.graw + (size_t)b1 * plane + (size_t)qy * W + qx;
-                        f4 vb; vb.x = v[0].y; vb.y = v[1].y; vb.z = v[2].y; vb.w = v[3].y;
-                        *reinterpret_cast<f4*>(pb) = vb;
-                    }
-                }
-            } }
-            // no barrier: the planes this pass reads (GY1) are next written by the following tile's B5
-        }
+        R2L_SYNC();   // planes are rewritten by the next tile
     }
 
     // ---- CTA reduction of the per-thread statistics into the kStat* layout (deterministic, fixed order) -------------
