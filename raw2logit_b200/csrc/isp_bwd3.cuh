@@ -23,7 +23,6 @@
 //     so the window the adjoint gather loads around q is reused for the statistic and only the centre value is read
 //     in addition; pad sites q outside the image belong to the nearest border tile; predicates are per run only.
 //     Q' is re-indexed to the p-based layout of kStatQ when the CTA writes its partial sums (finish_grad).
-// Shapes the fold pass cannot serve from one tile (a last tile row/column of <= 4 sites) go to the generic kernel.
 #pragma once
 #include <type_traits>
 #include "isp_fwd2.cuh"
@@ -106,8 +105,8 @@ template <int TH_, int TW_, int NT_, bool GRAW_, bool TAIL_, bool OUT_ = false> 
 
 // shapes the third generation serves (the rest goes to the generic scalar kernel)
 inline bool bwd3_shape_ok(int H, int W, int TH, int TW) {
-    const int rh = H % TH, rw = W % TW;
-    return (W % 4) == 0 && H >= 8 && W >= 8 && (rh == 0 || rh > 4) && (rw == 0 || rw > 4);
+    (void)TH; (void)TW;
+    return (W % 4) == 0 && H >= 8 && W >= 8;
 }
 
 template <class Cfg, typename RawT, bool TMA = false>
@@ -166,7 +165,6 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         const RawT* imgA = static_cast<const RawT*>(a.raw) + (size_t)b0 * plane;
         const RawT* imgB = static_cast<const RawT*>(a.raw) + (size_t)b1 * plane;
         const int e_top = ty0 == 0, e_bot = ty0 + TH >= H, e_lft = tx0 == 0, e_rgt = tx0 + TW >= W;
-        const bool border = e_top | e_bot | e_lft | e_rgt;
 
 #ifndef R2L_HOST_EMU
         if (TMA) {
@@ -559,106 +557,140 @@ R2L_HD void bwd3_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         R2L_SYNC();
         }
 
-        // ---- B5: gY1 on the padded domain = corr^T(gY2, Wg), rows -2..TH+1, runs -1..G; flipped Wg statistic --------
+        // ---- B5: gY1 = fold_reflect2(corr^T(gY2, Wg)) on rows -2..TH+1, runs -1..G (zero outside the image); dWg -----------
+        // The reflect-2 padding of the sharpened plane (pipeline_torch.py:165/202) folds pad rows -1,-2 / H,H+1 onto rows
+        // 1,2 / H-2,H-3 and likewise for columns.  A pad site's adjoint value only involves gY2 entries that lie inside
+        // the folded-onto site's own 5x5 window, and its Y1 value is the folded-onto site's own, so both the fold and the
+        // pad sites' share of the dWg statistic are a few extra products inside the items of those rows / columns
+        // (uniform per item): no pad items, no fold pass, no extra barrier.
+        //   pad row of target row ty, window row d (image row ty-2+d)  ->  tap row a' = 4 - 2 ty - d (top), mirrored below
+        //   pad column of target column tx: taps b <= 2 - tx (left), b >= 5 - j (right, j = site index in the last run)
         { R2L_FOR_THREADS(NT) {
             float wg[25];
 #pragma unroll
             for (int t = 0; t < 25; ++t) wg[t] = T->Wg[t];
             Bwd3Acc& acc = R2L_ACC(accs, tid);
-            // statistic domain: owned rectangle, extended over the pad ring on image-border sides (products vanish
-            // beyond the ring because gY2 is zero outside the image)
-            const int sr0 = e_top ? -2 : 0, sr1 = e_bot ? TH + 2 : TH, sg0 = e_lft ? -1 : 0, sg1 = e_rgt ? G + 1 : G;
             // one work item = NR runs of one row processed in lockstep (runs g and g + G/2): the statistic chains then
             // run over 4*NR sites before their horizontal add, and two independent windows are in flight per thread
             auto b5 = [&](auto NRc, int r, int g, bool stat) {
                 constexpr int NR = decltype(NRc)::value;
+                const int qy = ty0 + r;
                 f2 c[NR][4], out[NR][4];
+                bool inside[NR], lft[NR], rgt[NR];
+                bool any = false;
 #pragma unroll
                 for (int u = 0; u < NR; ++u) {
-                    ld4<PW>(Y1, (r + 6) * PW + 2 * (g + u * (G / 2) + 3), c[u]);
+                    const int qx = tx0 + 4 * (g + u * (G / 2));
+                    inside[u] = qy >= 0 && qy < H && qx >= 0 && qx < W;
+                    lft[u] = qx == 0; rgt[u] = qx + 4 == W;
+                    any |= inside[u];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) out[u][j] = mk2(0.f, 0.f);
                 }
+                if (any) {
 #pragma unroll
-                for (int d = 0; d < 5; ++d) {
-                    f2 row[NR][8];                                      // gY2 row q.y - 2 + d, columns q.x - 2 .. q.x + 5
+                    for (int u = 0; u < NR; ++u) {
+                        ld4<PW>(Y1, (r + 6) * PW + 2 * (g + u * (G / 2) + 3), c[u]);
+                        if (!inside[u]) {          // pad sites are accounted for by the folded-onto sites (below)
 #pragma unroll
-                    for (int u = 0; u < NR; ++u) ld8<PN>(PG, (r + 2 + d) * PN + 2 * (g + u * (G / 2) + 2), row[u]);
-                    const int aa = 4 - d;                               // tap row whose transpose reaches this row
+                            for (int j = 0; j < 4; ++j) c[u][j] = mk2(0.f, 0.f);
+                        }
+                    }
+                    // row type of the folded-onto rows: 1 -> row 1, 2 -> row 2, 3 -> row H-2, 4 -> row H-3
+                    const int rt = qy == 1 ? 1 : (qy == 2 ? 2 : (qy == H - 2 ? 3 : (qy == H - 3 ? 4 : 0)));
 #pragma unroll
-                    for (int u = 0; u < NR; ++u)
+                    for (int d = 0; d < 5; ++d) {
+                        f2 row[NR][8];                                  // gY2 row q.y - 2 + d, columns q.x - 2 .. q.x + 5
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                        for (int u = 0; u < NR; ++u) ld8<PN>(PG, (r + 2 + d) * PN + 2 * (g + u * (G / 2) + 2), row[u]);
+                        const int aa = 4 - d;                           // tap row whose transpose reaches this row
 #pragma unroll
-                            for (int bb = 0; bb < 5; ++bb) out[u][j] = fma2s(row[u][j + 4 - bb], wg[aa * 5 + bb], out[u][j]);
-                    if (stat) {
+                        for (int u = 0; u < NR; ++u)
 #pragma unroll
-                        for (int bb = 0; bb < 5; ++bb) {
-                            f2 t = mul2vv(c[0][0], row[0][4 - bb]);
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int bb = 0; bb < 5; ++bb) out[u][j] = fma2s(row[u][j + 4 - bb], wg[aa * 5 + bb], out[u][j]);
+                        float tsum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (stat) {
+#pragma unroll
+                            for (int bb = 0; bb < 5; ++bb) {
+                                f2 t = mul2vv(c[0][0], row[0][4 - bb]);
+#pragma unroll
+                                for (int u = 0; u < NR; ++u)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        if (u | j) t = fma2vv(c[u][j], row[u][j + 4 - bb], t);
+                                tsum[bb] = t.x + t.y;
+                                acc.wg[aa * 5 + bb] += tsum[bb];
+                            }
+                        }
+                        // pad columns of this window row, for tap row A (the regular one, or a pad row's)
+                        auto col_extra = [&](const int A) {      // A is a constant after unrolling / inlining
+#pragma unroll
+                            for (int u = 0; u < NR; ++u) {
+                                if (lft[u]) {        // pad columns -1 (-> site 1, taps b = 0,1) and -2 (-> site 2, tap b = 0)
+                                    out[u][1] = fma2s(row[u][3], wg[A * 5 + 0], fma2s(row[u][2], wg[A * 5 + 1], out[u][1]));
+                                    out[u][2] = fma2s(row[u][2], wg[A * 5 + 0], out[u][2]);
+                                    if (stat) {
+                                        const f2 t0 = fma2vv(c[u][1], row[u][3], mul2vv(c[u][2], row[u][2]));
+                                        const f2 t1 = mul2vv(c[u][1], row[u][2]);
+                                        acc.wg[A * 5 + 0] += t0.x + t0.y;
+                                        acc.wg[A * 5 + 1] += t1.x + t1.y;
+                                    }
+                                }
+                                if (rgt[u]) {        // pad columns W (-> site 2, taps b = 3,4) and W+1 (-> site 1, tap b = 4)
+                                    out[u][2] = fma2s(row[u][5], wg[A * 5 + 3], fma2s(row[u][4], wg[A * 5 + 4], out[u][2]));
+                                    out[u][1] = fma2s(row[u][5], wg[A * 5 + 4], out[u][1]);
+                                    if (stat) {
+                                        const f2 t3 = mul2vv(c[u][2], row[u][5]);
+                                        const f2 t4 = fma2vv(c[u][2], row[u][4], mul2vv(c[u][1], row[u][5]));
+                                        acc.wg[A * 5 + 3] += t3.x + t3.y;
+                                        acc.wg[A * 5 + 4] += t4.x + t4.y;
+                                    }
+                                }
+                            }
+                        };
+                        // a pad row reaches this window row through tap row A2
+                        auto row_extra = [&](const int A2) {
 #pragma unroll
                             for (int u = 0; u < NR; ++u)
 #pragma unroll
                                 for (int j = 0; j < 4; ++j)
-                                    if (u | j) t = fma2vv(c[u][j], row[u][j + 4 - bb], t);
-                            acc.wg[aa * 5 + bb] += t.x + t.y;
-                        }
+#pragma unroll
+                                    for (int bb = 0; bb < 5; ++bb) out[u][j] = fma2s(row[u][j + 4 - bb], wg[A2 * 5 + bb], out[u][j]);
+                            if (stat) {
+#pragma unroll
+                                for (int bb = 0; bb < 5; ++bb) acc.wg[A2 * 5 + bb] += tsum[bb];
+                            }
+                            col_extra(A2);                                   // corner pads
+                        };
+                        col_extra(aa);
+                        if (d == 0 && rt == 2) row_extra(0);
+                        if (d == 1 && rt == 1) row_extra(1);
+                        if (d == 2 && rt == 1) row_extra(0);
+                        if (d == 2 && rt == 3) row_extra(4);
+                        if (d == 3 && rt == 3) row_extra(3);
+                        if (d == 4 && rt == 4) row_extra(4);
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < NR; ++u)
+                for (int u = 0; u < NR; ++u) {
+                    if (!inside[u]) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) out[u][j] = mk2(0.f, 0.f);
+                    }
                     st4<PN>(GY1, (r + 2) * PN + 2 * (g + u * (G / 2) + 2), out[u][0], out[u][1], out[u][2], out[u][3]);
+                }
             };
             for (int item = tid; item < TH * (G / 2); item += NT)       // owned rectangle: one paired item per thread
                 b5(std::integral_constant<int, 2>(), item / (G / 2), item % (G / 2), true);
-            for (int item = TH * G + tid; item < Cfg::G1H * GG; item += NT) {      // halo ring, single runs
+            for (int item = TH * G + tid; item < Cfg::G1H * GG; item += NT) {      // halo ring, single runs, no statistic
                 int r, g;
                 region_item<TH, G, 2>(item, r, g);
-                b5(std::integral_constant<int, 1>(), r, g, r >= sr0 && r < sr1 && g >= sg0 && g < sg1);
+                b5(std::integral_constant<int, 1>(), r, g, false);
             }
         } }
         R2L_SYNC();
-        if (border) {
-            // fold of the reflect-2 padding: every in-image site within 2 of the border gathers its pad pre-images
-            // (which only it owns) and clears them, so gY1 is exact zero outside the image afterwards
-            { R2L_FOR_THREADS(NT) {
-                const int ry0 = ty0 - 2, ry1 = ty0 + TH + 2, rx0 = tx0 - 4, rx1 = tx0 + TW + 4;     // region of GY1
-                const int ya = imax(ry0, 0), yb = imin(ry1, H), xa = imax(rx0, 0), xb = imin(rx1, W);
-                const int nrow = yb - ya, ncol = xb - xa;
-                const int cand_y[4] = {1, 2, H - 3, H - 2}, cand_x[4] = {1, 2, W - 3, W - 2};
-                for (int i = tid; i < 4 * (ncol + nrow); i += NT) {
-                    int ty, tx;
-                    if (i < 4 * ncol) {                                 // target rows x all columns
-                        const int c = i / ncol;
-                        ty = cand_y[c]; tx = xa + (i - c * ncol);
-                        bool again = false;
-                        for (int c2 = 0; c2 < c; ++c2) again |= cand_y[c2] == ty;
-                        if (again || ty < ya || ty >= yb) continue;
-                    } else {                                            // target columns x the other rows
-                        const int i2 = i - 4 * ncol, c = i2 / nrow;
-                        tx = cand_x[c]; ty = ya + (i2 - c * nrow);
-                        bool again = false;
-                        for (int c2 = 0; c2 < c; ++c2) again |= cand_x[c2] == tx;
-                        if (again || tx < xa || tx >= xb) continue;
-                        int tmp[3];
-                        if (preimages2(ty, H, tmp) > 1) continue;      // a target row: handled above
-                    }
-                    int ys[3], xs[3];
-                    const int ny = preimages2(ty, H, ys), nx = preimages2(tx, W, xs);
-                    if (ny * nx == 1) continue;
-                    f2 s = mk2(0.f, 0.f);
-                    for (int iy = 0; iy < ny; ++iy)
-                        for (int ix = 0; ix < nx; ++ix) {
-                            const int py = ys[iy], px = xs[ix];
-                            if (py < ry0 || py >= ry1 || px < rx0 || px >= rx1) continue;
-                            f2& ref = site3<PN>(GY1, py - ry0, px - (tx0 - 8));
-                            s = add2v(s, ref);
-                            if (iy | ix) ref = mk2(0.f, 0.f);
-                        }
-                    site3<PN>(GY1, ty - ry0, tx - (tx0 - 8)) = s;
-                }
-            } }
-            R2L_SYNC();
-        }
 
         // ---- B6: gY0 = corr^T(gY1, Ws) (zero pad) on rows -1..TH, runs -1..G, zero outside the image; Ws statistic ----
         { R2L_FOR_THREADS(NT) {

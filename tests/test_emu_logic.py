@@ -131,7 +131,8 @@ def test_forward_v1_and_v2_agree_and_channel_statistics():
 
 @pytest.mark.parametrize("shape,n_cta,need_raw", [((3, 72, 136), 3, True), ((2, 64, 128), 3, True), ((1, 40, 72), 2, True),
                                                   ((3, 96, 200), 5, True), ((2, 8, 8), 1, True), ((2, 37, 8), 3, True),
-                                                  ((2, 64, 128), 3, False), ((1, 101, 72), 4, True)])
+                                                  ((2, 64, 128), 3, False), ((1, 101, 72), 4, True),
+                                                  ((2, 68, 132), 3, True), ((1, 33, 68), 2, True), ((1, 35, 196), 3, True)])
 def test_vectorised_backward_multi_tile_shapes(shape, n_cta, need_raw):
     """Third-generation backward (padded-domain phases + fold passes) on multi-tile / partial-tile / odd-batch shapes
     against the fp64 oracle."""
@@ -172,7 +173,8 @@ def test_forward_v3_multi_tile_shapes(shape, n_cta):
 
 
 @pytest.mark.parametrize("shape,n_cta,need_raw", [((3, 72, 136), 3, True), ((2, 64, 128), 3, False), ((1, 40, 72), 2, True),
-                                                  ((2, 8, 8), 1, True), ((1, 101, 72), 4, True)])
+                                                  ((2, 8, 8), 1, True), ((1, 101, 72), 4, True), ((2, 68, 132), 3, True),
+                                                  ((1, 33, 68), 2, True)])
 def test_backward_from_forward_output_matches_oracle(shape, n_cta, need_raw):
     """Backward variant that is handed the forward output (no Gaussian / colour-tail recompute): clip mask and gamma
     derivative are derived from the output; against the fp64 oracle and against the full-recompute kernel."""

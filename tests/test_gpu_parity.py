@@ -259,7 +259,8 @@ def test_tma_loader_and_generic_loader_agree_bitwise():
             assert torch.equal(au, bu), shape
 
 
-@pytest.mark.parametrize("shape", [(5, 256, 256), (2, 96, 200), (3, 72, 136), (1, 40, 8), (2, 37, 8), (4, 128, 192)])
+@pytest.mark.parametrize("shape", [(5, 256, 256), (2, 96, 200), (3, 72, 136), (1, 40, 8), (2, 37, 8), (4, 128, 192),
+                                   (2, 68, 132), (1, 33, 68)])
 @pytest.mark.parametrize("bn", [False, True])
 def test_vectorised_backward_agrees_with_generic_backward(shape, bn):
     """The third-generation backward (padded-domain phases, fold passes, TMA-fed) against the generic scalar kernel
