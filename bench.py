@@ -169,11 +169,15 @@ def run_ours(args):
     cam = syn.CAMERA_PRESETS[args.preset]
     mod = ParametrizedProcessing(cam, batch_norm_output=False).to(dev)
     base = syn.smooth_scene(B, H, W, args.preset, seed=1234 + rank)
+    vp0 = ctypes.c_void_p
     host_raw = [torch.roll(base, shifts=2 * s, dims=0).contiguous().pin_memory() for s in range(S)]
     raws = [h.to(dev) for h in host_raw]
     gouts = [torch.full((B, 3, H, W), 1.0 / (3 * pix), device=dev) * (1.0 + 0.01 * s) for s in range(S)]
     outs = [torch.empty(B, 3, H, W, device=dev) for _ in range(S)]
     graws = [torch.empty(B, H, W, device=dev) for _ in range(S)]
+    # Y0 / Y1 planes the forward keeps for the backward (8 B/px, r2l_isp.h: saved_luma)
+    lumas = [torch.empty(lib.r2l_isp_saved_luma_floats(B, H, W), device=dev) for _ in range(S)]
+    assert lib.r2l_isp_luma_supported(vp0(raws[0].data_ptr()), _lib.F32, B, H, W, vp0(outs[0].data_ptr()), None) == 1
     gpar = torch.empty(_lib.NUM_PARAM_GRADS, device=dev)
     nws = lib.r2l_isp_workspace_bytes(B, H, W)
     wsb = torch.empty(nws // 4, device=dev)
@@ -187,12 +191,13 @@ def run_ours(args):
     def step_kernels(i):
         s = i % S
         rc = lib.r2l_isp_forward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, H, W, ctypes.byref(params), None,
-                                 vp(outs[s].data_ptr()), sp)
+                                 vp(outs[s].data_ptr()), vp(lumas[s].data_ptr()), sp)
         return rc, s
 
     def step_backward(s):
         return lib.r2l_isp_backward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, H, W, ctypes.byref(params),
-                                    vp(gouts[s].data_ptr()), None, None, vp(outs[s].data_ptr()), vp(graws[s].data_ptr()),
+                                    vp(gouts[s].data_ptr()), None, None, vp(outs[s].data_ptr()),
+                                    vp(lumas[s].data_ptr()), vp(graws[s].data_ptr()),
                                     vp(gpar.data_ptr()), vp(wsb.data_ptr()), nws, sp)
 
     def barrier():
@@ -328,7 +333,7 @@ def run_ours(args):
         "e2e_uint16": {"value": e2e_u16_value, "unit": UNIT, "h2d_bytes_per_step": pix * 2, "d2h_bytes_per_step": 132 * 4,
                        "note": "same step with uint16 raw words over PCIe (normalised in the kernel); parameter "
                                "gradients only"},
-        "gpu_launches": 3 * K,
+        "gpu_launches": 2 * K,
         "roofline": {"bound": "hbm", "kernel": "isp_backward_kernel", "achieved": bwd_gbs, "peak": peak, "unit": "GB/s",
                      "frac": bwd_gbs / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_BWD * pix, "avg_launch_ms": bwd_ms},

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define R2L_ABI_VERSION 2
+#define R2L_ABI_VERSION 3
 
 enum {
     R2L_OK = 0,
@@ -87,8 +87,20 @@ int r2l_isp_last_cuda_error(void);
 /* Fused forward: replaces ParametrizedProcessing.forward (pipeline_torch.py:175-225) minus stage tracking:
  * raw2rgb :183 -> Debayer :187 -> WB :190 -> CCM :191 -> RGB2YUV :194 -> sharpen(Y) :195 -> Gaussian(Y) :202
  * -> YUV2RGB :203 -> clip :206 -> gamma :209 [-> additive :213] [-> eval-BN :217].  tail may be NULL. */
+/* saved_luma (NULL, or r2l_isp_saved_luma_floats(B,H,W) floats, 16-byte aligned): when given, the kernel also
+ * keeps the two luma planes it computes on the way -- Y0 (after RGB->YUV, :194) and Y1 (after the sharpening filter,
+ * :195) -- laid out [2][ceil(B/2)][H][W][2] (images 2p, 2p+1 interleaved per site; an odd last image is paired with
+ * itself).  They are what torch autograd would keep for the two convolutions' weight gradients; handing them to
+ * r2l_isp_backward lets it skip every recompute.  Only the vectorised kernel writes them: ask
+ * r2l_isp_luma_supported() first (R2L_ERR_BAD_ARGUMENT otherwise). */
 int r2l_isp_forward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
-                    const r2l_isp_params* params, const r2l_isp_tail* tail, float* out, void* stream);
+                    const r2l_isp_params* params, const r2l_isp_tail* tail, float* out, float* saved_luma,
+                    void* stream);
+size_t r2l_isp_saved_luma_floats(int B, int H, int W);
+/* 1 when a forward call with this raw / out / additive (pointer alignment, shape: W % 4 == 0, 16-byte aligned rows)
+ * takes the kernel that can write saved_luma, else 0 (then pass saved_luma = NULL to forward and backward). */
+int r2l_isp_luma_supported(const void* raw, int raw_dtype, int B, int H, int W, const float* out,
+                           const float* additive);
 
 /* Workspace every call below accepts (a fixed upper bound, independent of the shape). */
 size_t r2l_isp_workspace_bytes(int B, int H, int W);
@@ -101,7 +113,8 @@ size_t r2l_isp_workspace_bytes(int B, int H, int W);
 int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
                              const r2l_isp_params* params, const float* additive, float* out,
                              float* running_mean, float* running_var, float momentum, float eps,
-                             float* saved_affine, void* workspace, size_t workspace_bytes, void* stream);
+                             float* saved_affine, float* saved_luma, void* workspace, size_t workspace_bytes,
+                             void* stream);
 
 /* Backward of that tail, part 1: reduces sum(grad_out), sum(grad_out * out) per channel and writes the 15-float
  * grad_tail {gs[3], c1[3], c2[3], ysc[3], ysh[3]} that r2l_isp_backward consumes. */
@@ -118,11 +131,14 @@ int r2l_isp_bn_backward_prepare(const float* grad_out, const float* out, const f
  * keeps alive anyway): when given, the kernel derives the clip mask and the gamma derivative from it instead of
  * recomputing the Gaussian and the colour tail (about 20 % fewer instructions for 12 B/px more reads; the chip has
  * the bandwidth to spare).  With a tail, grad_tail's ysc/ysh and additive must describe the
- * affine map that produced out.  NULL = full recompute from raw. */
+ * affine map that produced out.  NULL = full recompute from raw.
+ * saved_luma (NULL or the planes the forward saved for the same call; only read together with out): the kernel then
+ * recomputes nothing -- no raw window, no Y0 / Y1 stencils -- and reads the three centre values its statistics need
+ * (Y1, Y0, raw) straight from memory; the 132 gradients are finished by the last CTA of the same launch. */
 int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
                      const r2l_isp_params* params, const float* grad_out, const float* grad_tail,
-                     const float* additive, const float* out, float* grad_raw, float* grad_params, void* workspace,
-                     size_t workspace_bytes, void* stream);
+                     const float* additive, const float* out, const float* saved_luma, float* grad_raw,
+                     float* grad_params, void* workspace, size_t workspace_bytes, void* stream);
 
 /* out[c][i] = scale[c] * sum_b x[b][c][i]  (scale may be NULL): gradient of the broadcast additive_layer
  * (pipeline_torch.py:212-214), x = grad_out (B,C,HW), out (C,HW).  Deterministic (fixed summation order). */

@@ -18,11 +18,12 @@ GRAD_LAYOUT = {
     "gauss_weight": (107, 25, (1, 1, 5, 5)),
 }
 F32, U16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = ("r2l_isp_abi_version", "r2l_isp_error_string", "r2l_isp_last_cuda_error", "r2l_isp_forward",
            "r2l_isp_workspace_bytes", "r2l_isp_forward_bn_train", "r2l_isp_bn_backward_prepare", "r2l_isp_backward",
-           "r2l_isp_mosaic", "r2l_isp_mosaic_backward", "r2l_isp_batch_sum")
+           "r2l_isp_mosaic", "r2l_isp_mosaic_backward", "r2l_isp_batch_sum", "r2l_isp_saved_luma_floats",
+           "r2l_isp_luma_supported")
 
 
 class IspParams(ctypes.Structure):
@@ -53,16 +54,21 @@ def load():
     lib.r2l_isp_error_string.argtypes = [ci]
     lib.r2l_isp_last_cuda_error.restype = ci
     lib.r2l_isp_forward.restype = ci
-    lib.r2l_isp_forward.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(IspParams), ctypes.POINTER(IspTail), vp, vp]
+    lib.r2l_isp_forward.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(IspParams), ctypes.POINTER(IspTail), vp, vp, vp]
+    lib.r2l_isp_saved_luma_floats.restype = sz
+    lib.r2l_isp_saved_luma_floats.argtypes = [ci, ci, ci]
+    lib.r2l_isp_luma_supported.restype = ci
+    lib.r2l_isp_luma_supported.argtypes = [vp, ci, ci, ci, ci, vp, vp]
     lib.r2l_isp_workspace_bytes.restype = sz
     lib.r2l_isp_workspace_bytes.argtypes = [ci, ci, ci]
     lib.r2l_isp_forward_bn_train.restype = ci
     lib.r2l_isp_forward_bn_train.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(IspParams), vp, vp, vp, vp, cf, cf,
-                                             vp, vp, sz, vp]
+                                             vp, vp, vp, sz, vp]
     lib.r2l_isp_bn_backward_prepare.restype = ci
     lib.r2l_isp_bn_backward_prepare.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, sz, vp]
     lib.r2l_isp_backward.restype = ci
-    lib.r2l_isp_backward.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(IspParams), vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.r2l_isp_backward.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(IspParams), vp, vp, vp, vp, vp, vp, vp, vp, sz,
+                                     vp]
     lib.r2l_isp_mosaic.restype = ci
     lib.r2l_isp_mosaic.argtypes = [vp, ci, cf, ci, ci, ci, vp, ci, ci, vp, vp]
     lib.r2l_isp_mosaic_backward.restype = ci

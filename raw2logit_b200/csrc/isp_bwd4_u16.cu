@@ -1,0 +1,7 @@
+// fourth-generation backward kernels, uint16 raw
+#include "isp_bwd4_tu.cuh"
+namespace r2l {
+int launch_backward4_u16(const BwdArgs& a, cudaStream_t st, int* grid_used) {
+    return launch_backward4_impl<uint16_t>(a, st, grid_used);
+}
+}  // namespace r2l

@@ -4,6 +4,7 @@
 #include "isp_fwd2.cuh"
 #include "isp_bwd3.cuh"
 #include "isp_fwd3.cuh"
+#include "isp_bwd4.cuh"
 
 namespace r2l {
 using FwdDefault = FwdCfg<32, 64, 256>;          // v1 (scalar) -- kept for the emulation cross-check only
@@ -13,5 +14,8 @@ using BwdNoRaw = BwdCfg<32, 64, 256, false>;     // v1 (scalar) -- emulation cro
 using BwdWithRaw = BwdCfg<32, 64, 256, true>;
 // v3: branch-free padded-domain phases; <TH, TW, NT, GRAW, TAIL, OUT (forward output available)>
 template <bool GRAW, bool TAIL, bool OUT = false> using Bwd3 = Bwd3Cfg<32, 64, 256, GRAW, TAIL, OUT>;
+// v4: forward output + saved Y0/Y1 planes, nothing recomputed, two CTAs per SM; <TH, TW, NT, GRAW, TAIL>
+template <bool GRAW, bool TAIL> using Bwd4 = Bwd4Cfg<32, 64, 128, GRAW, TAIL>;
+constexpr int kBwd4CtasPerSm = 2;
 constexpr int kMaxCtas = 2048;          // upper bound on persistent CTAs == rows of the statistics workspace
 }  // namespace r2l

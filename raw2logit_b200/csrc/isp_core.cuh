@@ -314,6 +314,8 @@ struct FwdArgs {
     const float* affine;       // {scale[3], shift[3]} or null
     float* out;
     float* chan_partials;      // STATS only: [n_cta][kChanPitch] per-CTA sums of o and o*o per channel
+    float* luma = nullptr;     // null, or [2][ceil(B/2)][H][W][2]: Y0 (plane 0) and Y1 (plane 1) of image pairs
+                               // (2p, 2p+1) interleaved per site, saved for the fourth-generation backward
 };
 constexpr int kChanPitch = 8;
 
@@ -463,6 +465,11 @@ struct BwdArgs {
     float* partials;       // [n_cta][kStatPitch]
     const float* out;      // null, or the forward's output (B,3,H,W): lets the vectorised backward skip the Gaussian /
                            // colour-tail recompute (the generic kernel ignores it)
+    const float* luma = nullptr;   // null, or the Y0 / Y1 planes the forward saved (FwdArgs::luma): with `out`, the
+                                   // fourth-generation backward recomputes nothing
+    unsigned* ticket = nullptr;    // device counter (zero on entry) for the fused finish: the last CTA to publish its
+                                   // partial sums turns them into the 132 gradients (null: separate finish kernel)
+    float* grads = nullptr;        // destination of the fused finish
 };
 
 // gather of the transposed 5x5 at a (possibly padded) site q': sum_ij Wg[ij] * gY2(q' - (i-2, j-2)), in-image only

@@ -157,6 +157,11 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[j][0] = mk2(0.f, 0.f);
                 }
+                else if (a.luma) {                     // owned, in the image: keep Y0 for the backward's dWs statistic
+                    float* dst = a.luma + (((size_t)(b0 >> 1) * H + (ty0 + r)) * W + (tx0 + 4 * g)) * 2;
+                    st2(reinterpret_cast<f2*>(dst), acc[0][0], acc[1][0]);
+                    st2(reinterpret_cast<f2*>(dst) + 2, acc[2][0], acc[3][0]);
+                }
                 st4<P>(Y0, (r + 3) * P + 2 * q, acc[0][0], acc[1][0], acc[2][0], acc[3][0]);
                 st4<TW>(U, r * TW + 2 * g, acc[0][1], acc[1][1], acc[2][1], acc[3][1]);
                 st4<TW>(V, r * TW + 2 * g, acc[0][2], acc[1][2], acc[2][2], acc[3][2]);
@@ -231,6 +236,11 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
                     for (int j = 0; j < 4; ++j)
 #pragma unroll
                         for (int bb = 0; bb < 3; ++bb) acc[j] = fma2s(in[j + bb], ws[aa * 3 + bb], acc[j]);
+                }
+                if (a.luma && rr >= 2 && rr < TH + 2 && g >= 0 && g < G && gy < H) {     // owned, in the image: keep Y1
+                    float* dst = a.luma + ((((size_t)((a.B + 1) >> 1) + (b0 >> 1)) * H + gy) * W + gx) * 2;
+                    st2(reinterpret_cast<f2*>(dst), acc[0], acc[1]);
+                    st2(reinterpret_cast<f2*>(dst) + 2, acc[2], acc[3]);
                 }
                 st4<P>(Y1, rr * P + 2 * q, acc[0], acc[1], acc[2], acc[3]);
                 if (gx == 0) { Y1[rr * P + phys<P>(4 * q - 1)] = acc[1]; Y1[rr * P + phys<P>(4 * q - 2)] = acc[2]; }

@@ -344,6 +344,20 @@ bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_bytes, int 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// the fused finish's ticket counter lives behind the per-CTA statistics rows of the workspace
+constexpr size_t kTicketOffset = (size_t)kMaxCtas * kStatPitch * sizeof(float);
+
+// does a forward call with these arguments run the kernel that can save the luma planes?  (one rule, used by
+// r2l_isp_forward, r2l_isp_forward_bn_train and r2l_isp_luma_supported)
+static bool luma_path_ok(const void* raw, int raw_dtype, int H, int W, const float* out, const float* additive) {
+    const char* force = getenv("R2L_ISP_FORCE_GENERIC");
+    if (force && force[0] == '1') return false;
+    if (const char* off = getenv("R2L_ISP_NO_TMA")) { if (off[0] == '1') return false; }
+    const int eb = raw_dtype == R2L_F32 ? 4 : 2;
+    return fwd3_shape_ok(H, W) && aligned(out, 16) && aligned(additive, 16) && aligned(raw, 16) &&
+           ((size_t)W * eb) % 16 == 0;
+}
+
 // statistics of the backward CTAs -> 132 gradients
 static int launch_finish(const BwdArgs& a, int n_cta, float* grads, cudaStream_t st) {
     isp_backward_finish_kernel<<<1, kFinishThreads, 0, st>>>(a.P, a.partials, n_cta, grads);
@@ -360,8 +374,16 @@ static int launch_backward_any(const BwdArgs& a, int raw_dtype, float* grads, cu
     int g = 0;
     int rc = kNotServed;
     const char* force = getenv("R2L_ISP_FORCE_GENERIC");        // debugging knob
-    if (!(force && force[0] == '1'))
-        rc = raw_dtype == R2L_F32 ? launch_backward3_f32(a, st, &g) : launch_backward3_u16(a, st, &g);
+    if (!(force && force[0] == '1')) {
+        if (a.out && a.luma) {                                  // fourth generation: nothing recomputed, fused finish
+            BwdArgs a4 = a;
+            a4.grads = grads;
+            a4.ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.partials) + kTicketOffset);
+            rc = raw_dtype == R2L_F32 ? launch_backward4_f32(a4, st, &g) : launch_backward4_u16(a4, st, &g);
+            if (rc == R2L_OK) return rc;
+        }
+        if (rc == kNotServed) rc = raw_dtype == R2L_F32 ? launch_backward3_f32(a, st, &g) : launch_backward3_u16(a, st, &g);
+    }
     if (rc == kNotServed) rc = launch_backward_generic(a, raw_dtype, st, &g);
     if (rc != R2L_OK) return rc;
     return launch_finish(a, g, grads, st);
@@ -392,13 +414,17 @@ const char* r2l_isp_error_string(int code) {
 int r2l_isp_last_cuda_error(void) { return g_last_cuda_error; }
 
 int r2l_isp_forward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
-                    const r2l_isp_params* params, const r2l_isp_tail* tail, float* out, void* stream) {
+                    const r2l_isp_params* params, const r2l_isp_tail* tail, float* out, float* saved_luma,
+                    void* stream) {
     int rc = check_common(raw, raw_dtype, B, H, W, params);
     if (rc != R2L_OK) return rc;
     if (B == 0) return R2L_OK;
     if (!out) return R2L_ERR_NULL_POINTER;
     if (!aligned(out, 4)) return R2L_ERR_MISALIGNED;
+    if (saved_luma && (!aligned(saved_luma, 16) || !luma_path_ok(raw, raw_dtype, H, W, out, tail ? tail->additive : nullptr)))
+        return R2L_ERR_BAD_ARGUMENT;                           // ask r2l_isp_luma_supported first
     FwdArgs a;
+    a.luma = saved_luma;
     a.raw = raw; a.denom = raw_denominator; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.additive = tail ? tail->additive : nullptr;
     a.affine = tail ? tail->affine : nullptr;
@@ -409,22 +435,36 @@ int r2l_isp_forward(const void* raw, int raw_dtype, float raw_denominator, int B
 
 size_t r2l_isp_workspace_bytes(int B, int H, int W) {
     (void)B; (void)H; (void)W;
-    return (size_t)kMaxCtas * kStatPitch * sizeof(float);
+    return kTicketOffset + 256;
+}
+
+size_t r2l_isp_saved_luma_floats(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return (size_t)4 * ((B + 1) / 2) * H * W;
+}
+
+int r2l_isp_luma_supported(const void* raw, int raw_dtype, int B, int H, int W, const float* out, const float* additive) {
+    if (B <= 0 || H < 3 || W < 3 || (raw_dtype != R2L_F32 && raw_dtype != R2L_U16)) return 0;
+    return luma_path_ok(raw, raw_dtype, H, W, out, additive) ? 1 : 0;
 }
 
 int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
                              const r2l_isp_params* params, const float* additive, float* out,
                              float* running_mean, float* running_var, float momentum, float eps,
-                             float* saved_affine, void* workspace, size_t workspace_bytes, void* stream) {
+                             float* saved_affine, float* saved_luma, void* workspace, size_t workspace_bytes,
+                             void* stream) {
     int rc = check_common(raw, raw_dtype, B, H, W, params);
     if (rc != R2L_OK) return rc;
     if (!out || !saved_affine || !workspace) return R2L_ERR_NULL_POINTER;
+    if (saved_luma && (!aligned(saved_luma, 16) || !luma_path_ok(raw, raw_dtype, H, W, out, additive)))
+        return R2L_ERR_BAD_ARGUMENT;
     if (!aligned(out, 4) || !aligned(workspace, 8)) return R2L_ERR_MISALIGNED;
     if (workspace_bytes < r2l_isp_workspace_bytes(B, H, W)) return R2L_ERR_WORKSPACE;
     if ((size_t)B * H * W < 2) return R2L_ERR_BAD_SHAPE;     // torch: "Expected more than 1 value per channel"
     FwdArgs a;
     a.raw = raw; a.denom = raw_denominator; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.additive = additive; a.affine = nullptr; a.out = out; a.chan_partials = static_cast<float*>(workspace);
+    a.luma = saved_luma;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int g = 0;
     rc = launch_forward_any(a, raw_dtype, true, st, &g);
@@ -457,8 +497,8 @@ int r2l_isp_bn_backward_prepare(const float* grad_out, const float* out, const f
 
 int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
                      const r2l_isp_params* params, const float* grad_out, const float* grad_tail,
-                     const float* additive, const float* out, float* grad_raw, float* grad_params, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+                     const float* additive, const float* out, const float* saved_luma, float* grad_raw,
+                     float* grad_params, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_common(raw, raw_dtype, B, H, W, params);
     if (rc != R2L_OK) return rc;
     if (!grad_params || !workspace || (B > 0 && !grad_out)) return R2L_ERR_NULL_POINTER;
@@ -474,6 +514,7 @@ int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int 
     a.raw = raw; a.denom = raw_denominator; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.gout = grad_out; a.gtail = grad_tail; a.additive = additive; a.graw = grad_raw; a.partials = static_cast<float*>(workspace);
     a.out = out;
+    a.luma = out ? saved_luma : nullptr;
     if (out && additive && !grad_tail) return R2L_ERR_BAD_ARGUMENT;   // an additive tail needs grad_tail to invert it
     return launch_backward_any(a, raw_dtype, grad_params, st);
 }

@@ -38,6 +38,9 @@ int launch_forward_u16(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_
 // third-generation backward (TMA-fed); returns kNotServed when the shape / alignment is not served
 int launch_backward3_f32(const BwdArgs& a, cudaStream_t st, int* grid_used);
 int launch_backward3_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
+// fourth-generation backward (forward output + saved luma planes, fused finish when a.ticket is set)
+int launch_backward4_f32(const BwdArgs& a, cudaStream_t st, int* grid_used);
+int launch_backward4_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
 // generic scalar kernels: any shape, any alignment
 int launch_backward_generic(const BwdArgs& a, int raw_dtype, cudaStream_t st, int* grid_used);
 constexpr int kNotServed = 1;

@@ -19,12 +19,14 @@ _PARAMS_SCHEMA = ("Tensor black_level, Tensor white_balance, Tensor colour_corre
                   "Tensor debayer_weight, Tensor sharpen_weight, Tensor gauss_weight, Tensor rgb2yuv, Tensor yuv2rgb")
 
 _library = torch.library.Library(_NS, "DEF")
-_library.define(f"forward(Tensor raw, {_PARAMS_SCHEMA}, Tensor? additive, Tensor? affine, float raw_denominator) -> Tensor")
+_library.define(f"forward(Tensor raw, {_PARAMS_SCHEMA}, Tensor? additive, Tensor? affine, float raw_denominator, "
+                "bool save_luma=False) -> (Tensor, Tensor)")
 _library.define(f"forward_bn_train(Tensor raw, {_PARAMS_SCHEMA}, Tensor? additive, Tensor(a!)? running_mean, "
-                "Tensor(b!)? running_var, float momentum, float eps, float raw_denominator) -> (Tensor, Tensor)")
+                "Tensor(b!)? running_var, float momentum, float eps, float raw_denominator, bool save_luma=False) "
+                "-> (Tensor, Tensor, Tensor)")
 _library.define("bn_backward_prepare(Tensor grad_out, Tensor out, Tensor saved_affine) -> Tensor")
 _library.define(f"backward(Tensor raw, {_PARAMS_SCHEMA}, Tensor grad_out, Tensor? grad_tail, Tensor? additive, "
-                "Tensor? out, bool need_raw_grad, float raw_denominator) -> (Tensor, Tensor)")
+                "Tensor? out, Tensor? luma, bool need_raw_grad, float raw_denominator) -> (Tensor, Tensor)")
 _library.define("mosaic(Tensor raw, Tensor? black_level, bool reduce_size, int out_channels, float raw_denominator) -> Tensor")
 _library.define("mosaic_backward(Tensor grad_out, int H, int W, bool reduce_size, int out_channels) -> Tensor")
 _library.define("batch_sum(Tensor x, Tensor? scale) -> Tensor")
@@ -74,7 +76,15 @@ def _check_shape(raw):
     return b, h, w
 
 
-def _forward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, affine, raw_denominator):
+def _luma_buffer(lib, raw, code, b, h, w, out, add, save_luma):
+    """The (2, ceil(B/2), H, W, 2) tensor for the Y0 / Y1 planes the forward keeps for the backward, or an empty
+    tensor when not asked for / when the call does not take the kernel that writes them (r2l_isp_luma_supported)."""
+    if save_luma and b > 0 and lib.r2l_isp_luma_supported(_ptr(raw), code, b, h, w, _ptr(out), _ptr(add)):
+        return torch.empty((2, (b + 1) // 2, h, w, 2), dtype=torch.float32, device=raw.device)
+    return torch.empty(0, dtype=torch.float32, device=raw.device)
+
+
+def _forward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, affine, raw_denominator, save_luma=False):
     lib = _lib.load()
     b, h, w = _check_shape(raw)
     raw, code = _raw_input(raw)
@@ -84,14 +94,15 @@ def _forward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, affine,
         aff = None if affine is None else _f32c(affine, 6, "affine")
         tail = _lib.IspTail(None if add is None else add.data_ptr(), None if aff is None else aff.data_ptr())
         out = torch.empty((b, 3, h, w), dtype=torch.float32, device=raw.device)
+        luma = _luma_buffer(lib, raw, code, b, h, w, out, add, save_luma)
         rc = lib.r2l_isp_forward(_ptr(raw), code, raw_denominator, b, h, w, ctypes.byref(params),
-                                 ctypes.byref(tail), _ptr(out), _stream())
+                                 ctypes.byref(tail), _ptr(out), _ptr(luma) if luma.numel() else None, _stream())
     _lib.check(rc, "r2l_isp_forward")
-    return out
+    return out, luma
 
 
 def _forward_bn_train_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, running_mean, running_var,
-                           momentum, eps, raw_denominator):
+                           momentum, eps, raw_denominator, save_luma=False):
     lib = _lib.load()
     b, h, w = _check_shape(raw)
     if b * h * w < 2:
@@ -107,11 +118,13 @@ def _forward_bn_train_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive
         saved = torch.empty(6, dtype=torch.float32, device=raw.device)
         nbytes = lib.r2l_isp_workspace_bytes(b, h, w)
         ws_buf = torch.empty(nbytes // 4, dtype=torch.float32, device=raw.device)
+        luma = _luma_buffer(lib, raw, code, b, h, w, out, add, save_luma)
         rc = lib.r2l_isp_forward_bn_train(_ptr(raw), code, raw_denominator, b, h, w, ctypes.byref(params), _ptr(add),
                                           _ptr(out), _ptr(running_mean), _ptr(running_var), momentum, eps,
-                                          _ptr(saved), _ptr(ws_buf), nbytes, _stream())
+                                          _ptr(saved), _ptr(luma) if luma.numel() else None, _ptr(ws_buf), nbytes,
+                                          _stream())
     _lib.check(rc, "r2l_isp_forward_bn_train")
-    return out, saved
+    return out, saved, luma
 
 
 def _bn_backward_prepare_cuda(grad_out, out, saved_affine):
@@ -130,7 +143,7 @@ def _bn_backward_prepare_cuda(grad_out, out, saved_affine):
     return tail
 
 
-def _backward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, grad_tail, additive, out, need_raw_grad,
+def _backward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, grad_tail, additive, out, luma, need_raw_grad,
                    raw_denominator):
     lib = _lib.load()
     b, h, w = _check_shape(raw)
@@ -141,12 +154,15 @@ def _backward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, grad_t
         gs = None if grad_tail is None else _f32c(grad_tail, 15, "grad_tail")
         add = None if additive is None else _f32c(additive, 3 * h * w, "additive")
         y = None if out is None else _f32c(out, b * 3 * h * w, "out")
+        lum = None
+        if luma is not None and luma.numel():
+            lum = _f32c(luma, lib.r2l_isp_saved_luma_floats(b, h, w), "luma")
         graw = torch.empty((b, h, w), dtype=torch.float32, device=raw.device) if need_raw_grad else None
         gpar = torch.empty(_lib.NUM_PARAM_GRADS, dtype=torch.float32, device=raw.device)
         nbytes = lib.r2l_isp_workspace_bytes(b, h, w)
         ws_buf = torch.empty(nbytes // 4, dtype=torch.float32, device=raw.device)
         rc = lib.r2l_isp_backward(_ptr(raw), code, raw_denominator, b, h, w, ctypes.byref(params), _ptr(g), _ptr(gs),
-                                  _ptr(add), _ptr(y), _ptr(graw), _ptr(gpar), _ptr(ws_buf), nbytes, _stream())
+                                  _ptr(add), _ptr(y), _ptr(lum), _ptr(graw), _ptr(gpar), _ptr(ws_buf), nbytes, _stream())
     _lib.check(rc, "r2l_isp_backward")
     if graw is None:
         graw = torch.empty(0, dtype=torch.float32, device=raw.device)
@@ -212,10 +228,12 @@ _ops = getattr(torch.ops, _NS)
 class FusedISP(torch.autograd.Function):
     """raw (B,H,W) + 7 parameter tensors + 2 buffers [+ additive] [+ BatchNorm tail] -> (B,3,H,W).
 
-    Saves ``raw``, the (tiny) parameters and the output tensor (which the consumer of the output keeps alive
-    anyway): the backward kernel recomputes Y0 / Y1 per tile from ``raw`` and reads the clip mask and the gamma
-    derivative off the saved output instead of recomputing the Gaussian and the colour tail (``R2L_ISP_RECOMPUTE=1``
-    makes it recompute everything from ``raw``).  Gradients are returned for raw (if needed), the 7 parameter
+    Saves ``raw``, the (tiny) parameters, the output tensor (which the consumer of the output keeps alive anyway)
+    and the two luma planes Y0 / Y1 the forward kernel computes on the way (8 B/px, what autograd would keep for the
+    two convolutions): the backward kernel then recomputes nothing -- the clip mask and the gamma derivative are read
+    off the saved output, the weight statistics read their Y1 / Y0 / raw centres from memory.
+    ``R2L_ISP_NO_LUMA=1`` keeps only the output (third-generation backward: Y0 / Y1 rebuilt per tile from ``raw``),
+    ``R2L_ISP_RECOMPUTE=1`` recomputes everything from ``raw``.  Gradients are returned for raw (if needed), the 7 parameter
     tensors and the additive layer; the colour-space buffers and the BatchNorm statistics get none, as in the
     reference.
 
@@ -228,17 +246,20 @@ class FusedISP(torch.autograd.Function):
                 momentum, eps, raw_denominator):
         params = (bl, wb, ccm, gamma, wd, ws, wg, m1, m2)
         saved_affine = None
+        # the backward reads the luma planes only together with the saved output (R2L_ISP_RECOMPUTE=1: neither)
+        save_luma = (os.environ.get("R2L_ISP_RECOMPUTE", "0") == "0" and os.environ.get("R2L_ISP_NO_LUMA", "0") != "1"
+                     and any(ctx.needs_input_grad[:8]))
         if bn_mode == 2:
-            out, saved_affine = _ops.forward_bn_train(raw, *params, additive, running_mean, running_var,
-                                                      momentum, eps, raw_denominator)
+            out, saved_affine, luma = _ops.forward_bn_train(raw, *params, additive, running_mean, running_var,
+                                                            momentum, eps, raw_denominator, save_luma)
             ctx.mark_non_differentiable(saved_affine)
         elif bn_mode == 1:
             scale = torch.rsqrt(running_var + eps)
             saved_affine = torch.cat([scale, -running_mean * scale])
-            out = _ops.forward(raw, *params, additive, saved_affine, raw_denominator)
+            out, luma = _ops.forward(raw, *params, additive, saved_affine, raw_denominator, save_luma)
         else:
-            out = _ops.forward(raw, *params, additive, None, raw_denominator)
-        ctx.save_for_backward(raw, *params, additive, saved_affine, out)
+            out, luma = _ops.forward(raw, *params, additive, None, raw_denominator, save_luma)
+        ctx.save_for_backward(raw, *params, additive, saved_affine, out, luma)
         ctx.bn_mode = bn_mode
         ctx.raw_denominator = raw_denominator
         return out
@@ -246,7 +267,7 @@ class FusedISP(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, saved_affine, out_saved = ctx.saved_tensors
+        raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, saved_affine, out_saved, luma = ctx.saved_tensors
         params = (bl, wb, ccm, gamma, wd, ws, wg, m1, m2)
         need_raw = ctx.needs_input_grad[0]
         grad_out = grad_out.contiguous()
@@ -264,7 +285,8 @@ class FusedISP(torch.autograd.Function):
         use_out = os.environ.get("R2L_ISP_RECOMPUTE", "0") != "1"
         if need_raw or any(ctx.needs_input_grad[1:8]):
             graw, gpar = _ops.backward(raw, *params, grad_out, tail, additive if tail is not None else None,
-                                       out_saved if use_out else None, need_raw, ctx.raw_denominator)
+                                       out_saved if use_out else None, luma if use_out else None, need_raw,
+                                       ctx.raw_denominator)
             if need_raw:
                 grads[0] = graw if raw.dtype == torch.float32 else graw.to(raw.dtype)
             for slot, name in enumerate(_lib.PARAM_FIELDS[:7], start=1):

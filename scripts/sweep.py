@@ -37,17 +37,18 @@ def main():
         outs = [torch.empty(B, 3, size, size, device=dev) for _ in range(S)]
         gouts = [torch.full((B, 3, size, size), 1.0 / (3 * pix), device=dev) for _ in range(S)]
         graws = [torch.empty(B, size, size, device=dev) for _ in range(S)]
+        lumas = [torch.empty(lib.r2l_isp_saved_luma_floats(B, size, size), device=dev) for _ in range(S)]
         nws = lib.r2l_isp_workspace_bytes(B, size, size)
         ws = torch.empty(nws // 4, device=dev)
 
         def fwd(s):
             return lib.r2l_isp_forward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, size, size, ctypes.byref(params),
-                                       None, vp(outs[s].data_ptr()), sp)
+                                       None, vp(outs[s].data_ptr()), vp(lumas[s].data_ptr()), sp)
 
         def bwd(s, need_raw):
             return lib.r2l_isp_backward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, size, size, ctypes.byref(params),
                                         vp(gouts[s].data_ptr()), None, None, vp(outs[s].data_ptr()),
-                                        vp(graws[s].data_ptr()) if need_raw else None, vp(gpar.data_ptr()),
+                                        vp(lumas[s].data_ptr()), vp(graws[s].data_ptr()) if need_raw else None, vp(gpar.data_ptr()),
                                         vp(ws.data_ptr()), nws, sp)
 
         def time_it(fn, n=12, warm=3):

@@ -13,6 +13,7 @@ DEPS = [SRC, os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_core.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_fwd2.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd3.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_fwd3.cuh"),
+        os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd4.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_config.h"), os.path.join(ROOT, "include", "r2l_isp.h")]
 
 PARAM_FIELDS = ["black_level", "white_balance", "colour_correction", "gamma_correct", "debayer.weight",
@@ -57,7 +58,8 @@ def _params(state):
     return p, keep
 
 
-def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0, version=3, chan_sums=None):
+def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0, version=3, chan_sums=None, luma=None):
+    """luma: optional float32 array (2, ceil(B/2), H, W, 2) that receives the saved Y0 / Y1 planes (version 3 only)."""
     raw = np.ascontiguousarray(raw)
     dtype = 1 if raw.dtype == np.uint16 else 0
     if dtype == 0:
@@ -70,13 +72,14 @@ def forward(raw, state, additive=None, affine=None, n_cta=3, denom=65535.0, vers
     out = np.full((b, 3, h, w), np.nan, dtype=np.float32)
     rc = lib().emu_isp_forward(ctypes.c_void_p(raw.ctypes.data), dtype, ctypes.c_float(denom), b, h, w,
                                ctypes.byref(p), ctypes.byref(tail), ctypes.c_void_p(out.ctypes.data), n_cta, version,
-                               None if chan_sums is None else ctypes.c_void_p(chan_sums.ctypes.data))
+                               None if chan_sums is None else ctypes.c_void_p(chan_sums.ctypes.data),
+                               None if luma is None else ctypes.c_void_p(luma.ctypes.data))
     assert rc == 0, rc
     return out
 
 
 def backward(raw, state, grad_out, need_raw_grad=True, n_cta=3, denom=65535.0, grad_tail=None, additive=None,
-             version=3, out=None):
+             version=3, out=None, luma=None):
     raw = np.ascontiguousarray(raw)
     dtype = 1 if raw.dtype == np.uint16 else 0
     if dtype == 0:
@@ -89,13 +92,15 @@ def backward(raw, state, grad_out, need_raw_grad=True, n_cta=3, denom=65535.0, g
     gs = None if grad_tail is None else _f32(grad_tail)
     add = None if additive is None else _f32(additive)
     outc = None if out is None else _f32(out)
+    lumac = None if luma is None else _f32(luma)
     rc = lib().emu_isp_backward(ctypes.c_void_p(raw.ctypes.data), dtype, ctypes.c_float(denom), b, h, w,
                                 ctypes.byref(p), ctypes.c_void_p(g.ctypes.data),
                                 None if gs is None else ctypes.c_void_p(gs.ctypes.data),
                                 None if add is None else ctypes.c_void_p(add.ctypes.data),
                                 None if graw is None else ctypes.c_void_p(graw.ctypes.data),
                                 ctypes.c_void_p(gpar.ctypes.data), n_cta, version,
-                                None if outc is None else ctypes.c_void_p(outc.ctypes.data))
+                                None if outc is None else ctypes.c_void_p(outc.ctypes.data),
+                                None if lumac is None else ctypes.c_void_p(lumac.ctypes.data))
     assert rc == 0, rc
     grads = {k: gpar[a:b_] for k, (a, b_) in GRAD_SLICES.items()}
     if graw is not None:

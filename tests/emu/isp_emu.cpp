@@ -51,7 +51,18 @@ static void run_backward(const BwdArgs& a, int n_cta, float* grads, int version)
         const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
         std::vector<float> smem(Cfg::kSmemFloats);
         for (int cta = 0; cta < n_cta; ++cta) bwd_cta<Cfg, RawT>(cta, n_cta, a, grid, smem.data());
-    } else if (version == 3) {
+    } else if (version == 4 && a.out && a.luma && bwd4_shape_ok(a.H, a.W)) {     // same dispatch rule as the CUDA launcher
+        auto go4 = [&](auto cfg) {
+            using C4 = decltype(cfg);
+            const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, C4::TH, C4::TW);
+            std::vector<float> smem(C4::kSmemBytes / 4 + 4);
+            float* base = smem.data();
+            while (reinterpret_cast<uintptr_t>(base) % 16) ++base;
+            for (int cta = 0; cta < n_cta; ++cta) bwd4_cta<C4, RawT>(cta, n_cta, a, grid, base);
+        };
+        if (a.gtail) go4(Bwd4<Cfg::GRAW, true>());
+        else go4(Bwd4<Cfg::GRAW, false>());
+    } else if (version == 3 || version == 4) {
         if (!bwd3_shape_ok(a.H, a.W, Cfg::TH, Cfg::TW)) {           // same dispatch rule as the CUDA launcher
             run_backward<Cfg, RawT>(a, n_cta, grads, 1);
             return;
@@ -87,9 +98,11 @@ extern "C" {
 
 // all pointers are HOST pointers here
 int emu_isp_forward(const void* raw, int raw_dtype, float denom, int B, int H, int W, const r2l_isp_params* params,
-                    const r2l_isp_tail* tail, float* out, int n_cta, int version, double* chan_sums) {
+                    const r2l_isp_tail* tail, float* out, int n_cta, int version, double* chan_sums, float* luma) {
     if (H < 3 || W < 3) return R2L_ERR_BAD_SHAPE;
+    if (luma && !(version == 3 && fwd3_shape_ok(H, W))) return R2L_ERR_BAD_ARGUMENT;
     FwdArgs a;
+    a.luma = luma;
     a.raw = raw; a.denom = denom; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.additive = tail ? tail->additive : nullptr; a.affine = tail ? tail->affine : nullptr; a.out = out;
     a.chan_partials = nullptr;
@@ -134,13 +147,14 @@ int emu_isp_forward(const void* raw, int raw_dtype, float denom, int B, int H, i
 
 int emu_isp_backward(const void* raw, int raw_dtype, float denom, int B, int H, int W, const r2l_isp_params* params,
                      const float* grad_out, const float* grad_tail, const float* additive, float* grad_raw,
-                     float* grad_params, int n_cta, int version, const float* out) {
+                     float* grad_params, int n_cta, int version, const float* out, const float* luma) {
     if (H < 3 || W < 3) return R2L_ERR_BAD_SHAPE;
     std::vector<float> partials((size_t)n_cta * kStatPitch, 0.f);
     BwdArgs a;
     a.raw = raw; a.denom = denom; a.B = B; a.H = H; a.W = W; a.P = to_params(params);
     a.gout = grad_out; a.gtail = grad_tail; a.additive = additive; a.graw = grad_raw; a.partials = partials.data();
     a.out = out;
+    a.luma = luma;
     if (grad_raw) {
         if (raw_dtype == R2L_F32) run_backward<BwdWithRaw, float>(a, n_cta, grad_params, version);
         else run_backward<BwdWithRaw, uint16_t>(a, n_cta, grad_params, version);

@@ -222,3 +222,89 @@ def test_backward_from_forward_output_golden_cases(name):
         scale = max(1.0, float(np.abs(r64).max()))
         assert maxabs(v.reshape(r64.shape), r64) <= 1e-4, (name, k)
         assert maxabs(v, ref[k]) <= 2e-5 * scale, (name, k, maxabs(v, ref[k]))
+
+
+# ---- fourth generation: the forward keeps Y0 / Y1, the backward recomputes nothing ------------------------------
+def _luma_oracle(raw, st):
+    """Y0 (after RGB->YUV, :194) and Y1 (after the sharpening filter, :195) in fp64, straight from the oracle's ops."""
+    import torch.nn.functional as F
+    s64 = isp_oracle.cast_state(st, torch.float64)
+    m = isp_oracle.mosaic(raw.double(), s64["black_level"], reduce_size=False, dtype=torch.float64)
+    d = F.conv2d(F.pad(m, (1, 1, 1, 1), mode="reflect"), s64["debayer.weight"])
+    c = isp_oracle._mix(d * s64["white_balance"].reshape(1, 3, 1, 1), s64["colour_correction"])
+    y0 = isp_oracle._mix(c, s64["M_RGB_2_YUV"])[:, 0]
+    y1 = F.conv2d(y0[:, None], s64["sharpening_filter.weight"], padding=1)[:, 0]
+    return y0.numpy(), y1.numpy()
+
+
+def _luma_alloc(b, h, w):
+    return np.full((2, (b + 1) // 2, h, w, 2), np.nan, dtype=np.float32)
+
+
+V4_SHAPES = [((3, 72, 136), 3, True), ((2, 64, 128), 3, False), ((1, 40, 72), 2, True), ((2, 8, 8), 1, True),
+             ((1, 101, 72), 4, True), ((2, 68, 132), 3, True), ((1, 33, 68), 2, True), ((2, 37, 8), 3, True),
+             ((3, 96, 200), 5, True)]
+
+
+@pytest.mark.parametrize("shape,n_cta,need_raw", V4_SHAPES)
+def test_saved_luma_planes_and_v4_backward(shape, n_cta, need_raw):
+    """The forward's saved luma planes equal the oracle's Y0 / Y1 (pair-interleaved layout, odd batches duplicate the
+    last image), and the fourth-generation backward fed with them matches the fp64 oracle and the third generation."""
+    raw = syn.smooth_scene(*shape, "drone", seed=sum(shape) + 2)
+    st = syn.perturbed_state(isp_oracle.default_state(syn.CAMERA_PRESETS["drone"]))
+    b, h, w = shape
+    luma = _luma_alloc(b, h, w)
+    out = emu.forward(raw.numpy(), st, n_cta=n_cta, version=3, luma=luma)
+    assert not np.isnan(luma).any()
+    y0, y1 = _luma_oracle(raw, st)
+    for img in range(b):
+        assert maxabs(luma[0, img // 2, :, :, img % 2], y0[img]) <= 2e-6
+        assert maxabs(luma[1, img // 2, :, :, img % 2], y1[img]) <= 2e-6
+    if b % 2:
+        assert np.array_equal(luma[:, -1, :, :, 1], luma[:, -1, :, :, 0])
+    want, grads = isp_oracle.forward_backward(raw, st, grad_out="ramp", dtype=torch.float64)
+    g = isp_oracle.cotangent(tuple(want.shape), "ramp").numpy()
+    got = emu.backward(raw.numpy(), st, g, n_cta=n_cta, need_raw_grad=need_raw, out=out, luma=luma, version=4)
+    ref = emu.backward(raw.numpy(), st, g, n_cta=n_cta, need_raw_grad=need_raw, out=out, version=3)
+    for k, v in got.items():
+        r64 = grads[k].numpy()
+        scale = max(1.0, float(np.abs(r64).max()))
+        assert maxabs(v.reshape(r64.shape), r64) <= 5e-6 * scale, (k, shape)
+        assert maxabs(v, ref[k]) <= 5e-6 * scale, (k, shape)
+
+
+@pytest.mark.parametrize("name", ["bn_train", "bn_train_additive", "noise_g2_pert", "car_crop", "impulses", "drone_g1_pert",
+                                  "micro_g1_pert"])
+def test_v4_backward_golden_cases(name):
+    """Fourth generation on the golden cases (clip-heavy inputs, BatchNorm / additive tails, impulses at every CFA
+    phase and border)."""
+    c = GoldenCase(name)
+    cot = "ramp"
+    b, h, w = c.raw.shape
+    if w % 4 or h < 8 or w < 8:
+        pytest.skip("shape is served by the generic kernel")
+    luma = _luma_alloc(b, h, w)
+    if c.bn is None:
+        g = isp_oracle.cotangent(tuple(c.f32["out"].shape), cot).numpy()
+        add = None if c.additive is None else c.additive.numpy()[0]
+        out = emu.forward(c.raw.numpy(), c.state, additive=add, luma=luma)
+        tail = None
+        if add is not None:
+            tail = np.asarray([1, 1, 1, 0, 0, 0, 0, 0, 0, 1, 1, 1, 0, 0, 0], dtype=np.float32)
+        got = emu.backward(c.raw.numpy(), c.state, g, out=out, luma=luma, version=4, grad_tail=tail, additive=add)
+    else:
+        add = None if c.additive is None else c.additive
+        emu.forward(c.raw.numpy(), c.state, additive=None if add is None else add.numpy()[0], luma=luma)
+        o, _ = isp_oracle.forward(c.raw.double(), isp_oracle.cast_state(c.state, torch.float64),
+                                  additive=None if add is None else add.double(), dtype=torch.float64)
+        mean, var = o.mean(dim=(0, 2, 3)), o.var(dim=(0, 2, 3), unbiased=False)
+        inv = 1.0 / torch.sqrt(var + 1e-5)
+        y = (o - mean.view(1, 3, 1, 1)) * inv.view(1, 3, 1, 1)
+        gt = isp_oracle.cotangent(tuple(y.shape), cot, torch.float64)
+        tail = torch.cat([inv, gt.mean(dim=(0, 2, 3)), (gt * y).mean(dim=(0, 2, 3)), inv, -mean * inv]).float().numpy()
+        addn = None if add is None else add.numpy()[0]
+        got = emu.backward(c.raw.numpy(), c.state, gt.float().numpy(), grad_tail=tail, additive=addn,
+                           out=y.float().numpy(), luma=luma, version=4)
+    for k, v in got.items():
+        r64 = c.f64[f"grad.{cot}.{k}"]
+        assert maxabs(v.reshape(r64.shape), r64) <= 1e-4, (name, k)

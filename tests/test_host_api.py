@@ -24,7 +24,7 @@ def test_library_exports_every_symbol_the_header_declares(lib):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.r2l_isp_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.r2l_isp_abi_version() == _lib.ABI_VERSION == 3
     assert b"shape" in lib.r2l_isp_error_string(-1)
     assert lib.r2l_isp_workspace_bytes(64, 256, 256) >= 155 * 4
 
@@ -32,9 +32,9 @@ def test_library_exports_every_symbol_the_header_declares(lib):
 def test_argument_validation_happens_before_any_cuda_call(lib):
     import ctypes
     p = _lib.IspParams(*([1] * 9))
-    assert lib.r2l_isp_forward(None, 7, 65535.0, 1, 8, 8, ctypes.byref(p), None, None, None) == -2   # dtype
-    assert lib.r2l_isp_forward(None, 0, 65535.0, 1, 2, 8, ctypes.byref(p), None, None, None) == -1   # H < 3
-    assert lib.r2l_isp_forward(None, 0, 65535.0, 1, 8, 8, ctypes.byref(p), None, None, None) == -3   # null raw
+    assert lib.r2l_isp_forward(None, 7, 65535.0, 1, 8, 8, ctypes.byref(p), None, None, None, None) == -2   # dtype
+    assert lib.r2l_isp_forward(None, 0, 65535.0, 1, 2, 8, ctypes.byref(p), None, None, None, None) == -1   # H < 3
+    assert lib.r2l_isp_forward(None, 0, 65535.0, 1, 8, 8, ctypes.byref(p), None, None, None, None) == -3   # null raw
     assert lib.r2l_isp_mosaic(None, 0, 1.0, 1, 7, 8, None, 1, 3, None, None) == -1                   # odd + packed
     assert lib.r2l_isp_mosaic(None, 0, 1.0, 1, 8, 8, None, 1, 5, None, None) == -7                   # channels
 
