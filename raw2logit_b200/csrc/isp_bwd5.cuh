@@ -1,0 +1,633 @@
+// isp_bwd5.cuh -- fifth-generation fused backward: the statistics live in tensor memory.
+//
+// Reference: the autograd graph of pipeline_torch.py:183-217.  Same phases, planes, border rules and
+// adjoint algebra as the fourth generation (isp_bwd4.cuh: nothing recomputed, forward output + saved luma planes), but
+// the 96 per-thread running sums behind the 132 parameter gradients no longer occupy registers for the whole launch:
+//   * they are parked in TMEM (isp_tmem.cuh: one private 32-bit cell per thread and column) and a phase loads only the
+//     group it updates -- B4 the gamma sum, B5 the 25 Gaussian taps, B6 the 9 sharpening taps, B7 one YUV channel's
+//     20 demosaic sums at a time -- and stores it back when it ends;
+//   * with at most 36 sums live, the kernel fits 128 registers: 256 threads x 2 CTAs per SM = 16 warps (was 8 at
+//     255 registers with spills, profiles/r01_v4_summary.md), so the global loads of one warp hide behind the
+//     stencils of three others;
+//   * B7 walks the three gradient planes one after the other (k outermost) with packed (image A, image B)
+//     accumulators: the Q' statistic is one FFMA2 per tap and site pair instead of two scalar FMAs;
+//   * stencil weights are read from shared memory next to their use (uniform-address LDS) instead of sitting in
+//     25 / 54 registers for a whole phase.
+// Column layout per thread (also the order of the host emulation's array and of the CTA reduction):
+//   [0,2) gamma sum per stream | [2,27) dWg | [27,36) dWs | [36 + 20 k, +18) Q'[k][tap row][col phase][b] | (+18, +2) P[k][col phase]
+#pragma once
+#include "isp_bwd4.cuh"
+#include "isp_tmem.cuh"
+
+namespace r2l {
+
+constexpr int kB5Sg = 0, kB5Wg = 2, kB5Ws = 27, kB5Q = 36, kB5QStride = 20, kBwd5AccFloats = 96;
+
+template <int TH_, int TW_, int NT_, bool GRAW_, bool TAIL_> struct Bwd5Cfg : Bwd4Cfg<TH_, TW_, NT_, GRAW_, TAIL_> {
+    static constexpr int kAccCols = (NT_ / 128) * kBwd5AccFloats;          // warps w and w + 4 share TMEM lanes
+    static constexpr int kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : kAccCols <= 256 ? 256 : 512;
+    static_assert(NT_ % 128 == 0 && kAccCols <= 512, "whole warpgroups; the sums must fit the CTA's TMEM columns");
+    static_assert(((TH_ / 2) * (TW_ / 4)) % (NT_ / 2) == 0, "B7: the same number of items for every thread");
+};
+
+inline bool bwd5_shape_ok(int H, int W) { return bwd4_shape_ok(H, W); }
+
+// (x, y) -> one aligned register pair, materialised once (a plain make_float2 of values from two different loads is
+// re-packed with two MOVs at every FFMA2 that uses it when registers are tight)
+R2L_HD f2 pack2(float x, float y) {
+#ifdef R2L_HOST_EMU
+    return mk2(x, y);
+#else
+    unsigned long long r;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    f2 o;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+    return o;
+#endif
+}
+
+// a phase's view of its running sums: load at phase start, store at phase end
+#ifdef R2L_HOST_EMU
+#define R2L_PARK_LOAD(N, col, v)  { const float* s_ = accs[tid].sums + (col); for (int i_ = 0; i_ < (N); ++i_) (v)[i_] = s_[i_]; }
+#define R2L_PARK_STORE(N, col, v) { float* s_ = accs[tid].sums + (col); for (int i_ = 0; i_ < (N); ++i_) s_[i_] = (v)[i_]; }
+struct Bwd5Acc { float sums[kBwd5AccFloats]; };
+#else
+#define R2L_PARK_LOAD(N, col, v)  { __syncwarp(); tmem::load<N>(tacc + (col), v); tmem::wait_ld(); }
+#define R2L_PARK_STORE(N, col, v) { __syncwarp(); tmem::store<N>(tacc + (col), v); tmem::wait_st(); }
+#endif
+
+template <class Cfg, typename RawT>
+R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid, float* smem) {
+    constexpr int TH = Cfg::TH, TW = Cfg::TW, NT = Cfg::NT, PN = Cfg::PN, G = Cfg::G, HALF = Cfg::HALF;
+    constexpr int GG = G + 2;                                     // runs -1 .. G
+    Tables2* T2 = reinterpret_cast<Tables2*>(smem);
+    Tables* T = &T2->base;
+    f2* PU = reinterpret_cast<f2*>(smem + Cfg::kTableFloats);     // gU
+    f2* PV = PU + Cfg::kF;                                        // gV
+    f2* PG = PV + Cfg::kF;                                        // gY2, then gY0
+    f2* GY1 = PG + Cfg::kF;                                       // gY1
+#ifdef R2L_HOST_EMU
+    std::vector<Bwd5Acc> accs(NT);
+    std::memset(accs.data(), 0, sizeof(Bwd5Acc) * NT);
+#else
+    // TMEM columns for the running sums: warp 0 allocates, everybody zeroes its own cells
+    __shared__ uint32_t tmem_slot;
+    if (threadIdx.x < 32) tmem::alloc<Cfg::kTmemCols>(&tmem_slot);
+    tmem::fence_before_sync();
+    __syncthreads();
+    tmem::fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tacc = tmem::addr(tmem_base, (int)(threadIdx.x >> 7) * kBwd5AccFloats);
+    {
+        float z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < kBwd5AccFloats; c0 += 16) tmem::store<16>(tacc + c0, z);
+        tmem::wait_st();
+    }
+#endif
+    const int H = a.H, W = a.W;
+    const size_t plane = (size_t)H * W;
+    const size_t luma_plane = (size_t)((a.B + 1) >> 1) * plane * 2;      // floats per saved plane
+    // planes start finite: never-written pad columns are read by don't-care items
+    { R2L_FOR_THREADS(NT) {
+        for (int i = tid; i < Cfg::kSites; i += NT) PU[i] = mk2(0.f, 0.f);
+    } }
+    R2L_BUILD_TABLES(NT, a.P, T)
+    { R2L_FOR_THREADS(NT) { build_tables2_extra(tid, NT, T2); } }
+    R2L_SYNC();
+    for (int tile = cta; tile < grid.n; tile += n_cta) {
+        int b0, b1, ty0, tx0;
+        decode_pair_tile(grid, tile, TH, TW, a.B, b0, b1, ty0, tx0);
+        const bool dup = b1 == b0;
+        const RawT* imgA = static_cast<const RawT*>(a.raw) + (size_t)b0 * plane;
+        const RawT* imgB = static_cast<const RawT*>(a.raw) + (size_t)b1 * plane;
+        const float* y0pair = a.luma + (size_t)(b0 >> 1) * plane * 2;   // Y0 of this image pair, [H][W][2]
+        const float* y1pair = y0pair + luma_plane;
+
+        // ---- B4: grad_out pulled back through gamma / clip / YUV->RGB to (gY2, gU, gV) on rows -4..TH+3, runs -1..G;
+        // gamma statistic.  o = y (or (y - shift)/scale - additive behind a tail); with lo = log2(o):
+        // e = cl^(1/g - 1) = 2^((1 - g) lo), log2(cl) = g lo, and the clamp passed iff o lies strictly between its two
+        // clipped values (exact compare without a tail, where o is bit-identical to the forward's; a 1e-4 / 1e-6
+        // relative margin behind a tail, where o is recovered by an affine inverse).
+        { R2L_FOR_THREADS(NT) {
+#ifndef R2L_HOST_EMU
+            // the centres B5 / B6 / B7 read from global memory (Y1, Y0, raw of the owned rows): pull their lines into L2
+            {
+                constexpr int LPR = TW * 8 / 128;                      // 128-byte lines per owned row of a luma plane
+                for (int i = tid; i < TH * LPR * 2; i += NT) {
+                    const int l = i % LPR, rr = (i / LPR) % TH, pl = i / (LPR * TH);
+                    const int gy = ty0 + rr, gx = tx0 + l * 16;
+                    if (gy < H && gx < W) prefetch_l2((pl ? y1pair : y0pair) + ((size_t)gy * W + gx) * 2);
+                }
+                constexpr int RPL = 128 / (int)sizeof(RawT);           // raw elements per line
+                constexpr int LPRR = (TW + RPL - 1) / RPL;
+                for (int i = tid; i < TH * LPRR * 2; i += NT) {
+                    const int l = i % LPRR, rr = (i / LPRR) % TH, im = i / (LPRR * TH);
+                    const int gy = ty0 + rr, gx = tx0 + l * RPL;
+                    if (gy < H && gx < W) prefetch_l2((im ? imgB : imgA) + (size_t)gy * W + gx);
+                }
+            }
+#endif
+            float m2g[9];
+            const float invg = T->invg, gam = T->gamma, one_m_g = 1.0f - T->gamma;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) m2g[t] = T->M2[t] * invg;
+            const float o_lo_exact = fast_exp2(invg * fast_log2(kClipLo));      // the forward's value of a low clip
+            const float o_lo = Cfg::TAIL ? o_lo_exact * (1.0f + 1e-4f) : o_lo_exact;
+            const float o_hi = Cfg::TAIL ? 1.0f - 1e-6f : 1.0f;
+            f2 sg = mk2(0.f, 0.f);                                     // sum G o log2(cl), per stream
+            for (int item = tid; item < Cfg::FH * GG; item += NT) {
+                const int rr = item / GG, g = item - rr * GG - 1;
+                const int r = rr - 4;
+                const int gy = ty0 + r, gx = tx0 + 4 * g;
+                const bool valid = gy >= 0 && gy < H && gx >= 0 && gx < W;
+                const bool owned = r >= 0 && r < TH && g >= 0 && g < G;
+                f2 gy2[4], gu[4], gv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { gy2[j] = mk2(0.f, 0.f); gu[j] = mk2(0.f, 0.f); gv[j] = mk2(0.f, 0.f); }
+                if (valid) {
+                    const size_t pix = (size_t)gy * W + gx;
+                    f4 ga[3], gb[3], ya[3], yb[3], ad[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const size_t oa = ((size_t)b0 * 3 + k) * plane + pix, ob = ((size_t)b1 * 3 + k) * plane + pix;
+                        ga[k] = ld_stream4(a.gout + oa);
+                        ya[k] = ld_stream4(a.out + oa);
+                        gb[k] = ld_stream4(a.gout + ob);
+                        yb[k] = ld_stream4(a.out + ob);
+                        ad[k].x = ad[k].y = ad[k].z = ad[k].w = 0.f;
+                        if (Cfg::TAIL && a.additive) ad[k] = *reinterpret_cast<const f4*>(a.additive + (size_t)k * plane + pix);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float gak[4] = {ga[k].x, ga[k].y, ga[k].z, ga[k].w}, gbk[4] = {gb[k].x, gb[k].y, gb[k].z, gb[k].w};
+                        const float yak[4] = {ya[k].x, ya[k].y, ya[k].z, ya[k].w}, ybk[4] = {yb[k].x, yb[k].y, yb[k].z, yb[k].w};
+                        const float adk[4] = {ad[k].x, ad[k].y, ad[k].z, ad[k].w};
+                        float t_gs = 1.f, t_c1 = 0.f, t_c2 = 0.f, t_isc = 1.f, t_osh = 0.f;
+                        if (Cfg::TAIL) {
+                            t_gs = a.gtail[k]; t_c1 = a.gtail[3 + k]; t_c2 = a.gtail[6 + k];
+                            t_isc = 1.0f / a.gtail[9 + k]; t_osh = -a.gtail[12 + k] * t_isc;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float Ga = gak[j], Gb = dup ? 0.f : gbk[j];
+                            f2 o = mk2(yak[j], ybk[j]);
+                            if (Cfg::TAIL) {
+                                Ga = t_gs * (Ga - t_c1 - t_c2 * o.x);
+                                Gb = dup ? 0.f : t_gs * (Gb - t_c1 - t_c2 * o.y);
+                                o = mk2(fmaf_(o.x, t_isc, t_osh) - adk[j], fmaf_(o.y, t_isc, t_osh) - adk[j]);
+                            }
+                            const f2 lo = mk2(fast_log2(o.x), fast_log2(o.y));
+                            const f2 ex = mul2s(lo, one_m_g);
+                            const f2 e = mk2(fast_exp2(ex.x), fast_exp2(ex.y));
+                            if (owned) sg = fma2vv(mk2(Ga * o.x, Gb * o.y), mul2s(lo, gam), sg);
+                            const f2 gr = mk2((o.x > o_lo && o.x < o_hi) ? Ga * e.x : 0.f,
+                                              (o.y > o_lo && o.y < o_hi) ? Gb * e.y : 0.f);
+                            gy2[j] = fma2s(gr, m2g[k * 3 + 0], gy2[j]);
+                            gu[j] = fma2s(gr, m2g[k * 3 + 1], gu[j]);
+                            gv[j] = fma2s(gr, m2g[k * 3 + 2], gv[j]);
+                        }
+                    }
+                }
+                st4<PN>(PG, (r + 4) * PN + 2 * (g + 2), gy2[0], gy2[1], gy2[2], gy2[3]);
+                st4<PN>(PU, (r + 4) * PN + 2 * (g + 2), gu[0], gu[1], gu[2], gu[3]);
+                st4<PN>(PV, (r + 4) * PN + 2 * (g + 2), gv[0], gv[1], gv[2], gv[3]);
+            }
+            {
+                float v[2];
+                R2L_PARK_LOAD(2, kB5Sg, v)
+                v[0] += sg.x; v[1] += sg.y;
+                R2L_PARK_STORE(2, kB5Sg, v)
+            }
+        } }
+        R2L_SYNC();
+
+        // ---- B5: gY1 = fold_reflect2(corr^T(gY2, Wg)) on rows -2..TH+1, runs -1..G (zero outside the image); dWg ----
+        // Border rules as in isp_bwd3.cuh B5: the reflect-2 fold and the pad sites' share of dWg are a few extra products
+        // inside the items of rows 1,2 / H-2,H-3 and of the first / last run of the image.  Y1 centres come from the
+        // plane the forward saved.
+        { R2L_FOR_THREADS(NT) {
+#ifndef R2L_HOST_EMU
+            // next tile's grad_out / forward-output windows (rows -4..TH+3 of 3 channels x 2 images x 2 tensors) -> L2
+            {
+                const int next = tile + n_cta;
+                if (next < grid.n) {
+                    int nb0, nb1, ny0, nx0;
+                    decode_pair_tile(grid, next, TH, TW, a.B, nb0, nb1, ny0, nx0);
+                    constexpr int LPR = TW * 4 / 128;
+                    const int nl = Cfg::FH * 12 * LPR;
+                    for (int i = tid; i < nl; i += NT) {
+                        const int l = i % LPR, pr = i / LPR, pk = pr % 12, rr = pr / 12;
+                        const int gy = ny0 - 4 + rr, gx = nx0 + l * 32;
+                        const int pk6 = pk % 6, img = pk6 < 3 ? nb0 : nb1, k = pk6 < 3 ? pk6 : pk6 - 3;
+                        if (gy >= 0 && gy < H && gx < W)
+                            prefetch_l2((pk < 6 ? a.gout : a.out) + ((size_t)img * 3 + k) * plane + (size_t)gy * W + gx);
+                    }
+                }
+            }
+#endif
+            // The weights are read next to their use (uniform-address LDS; volatile keeps the compiler from hoisting all
+            // 25 into registers for the whole phase).
+            const volatile float* wg = T->Wg;
+            // -- owned rectangle (the items that carry the statistic): one TAP ROW A of the 5x5 at a time over all of the
+            // thread's items, so only that row's five packed (image A, image B) sums are live (parked per tap row).
+            // Tap row A reaches window row 4 - A; the folded pad contributions that use tap row A ride in the same pass.
+            {
+                constexpr int NI5 = TH * G / NT;
+                static_assert((TH * G) % NT == 0, "B5: the same number of owned items for every thread");
+                f2 c[NI5][4], out[NI5][4];
+                int ir[NI5], ig[NI5], rt[NI5];
+                bool inside[NI5], lft[NI5], rgt[NI5];
+#pragma unroll
+                for (int u = 0; u < NI5; ++u) {
+                    const int item = tid + u * NT;
+                    const int r = item / G, g = item - r * G;
+                    const int qy = ty0 + r, qx = tx0 + 4 * g;
+                    ir[u] = r; ig[u] = g;
+                    inside[u] = qy < H && qx < W;
+                    lft[u] = qx == 0; rgt[u] = qx + 4 == W;
+                    // row type of the folded-onto rows: 1 -> row 1, 2 -> row 2, 3 -> row H-2, 4 -> row H-3
+                    rt[u] = qy == 1 ? 1 : (qy == 2 ? 2 : (qy == H - 2 ? 3 : (qy == H - 3 ? 4 : 0)));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { out[u][j] = mk2(0.f, 0.f); c[u][j] = mk2(0.f, 0.f); }
+                    if (inside[u]) ld_luma4(y1pair + ((size_t)qy * W + qx) * 2, c[u]);
+                }
+#pragma unroll
+                for (int A = 0; A < 5; ++A) {
+                    f2 acc[5];
+                    {
+                        float wa[5];
+                        R2L_PARK_LOAD(5, kB5Wg + 5 * A, wa)
+#pragma unroll
+                        for (int bb = 0; bb < 5; ++bb) acc[bb] = mk2(wa[bb], 0.f);
+                    }
+                    float w5[5];
+#pragma unroll
+                    for (int bb = 0; bb < 5; ++bb) w5[bb] = wg[A * 5 + bb];
+#pragma unroll
+                    for (int u = 0; u < NI5; ++u) {
+                        if (!inside[u]) continue;
+                        // products of one window row with tap row A: adjoint, statistic, and (first / last run of the
+                        // image) the pad columns' share: -1 -> site 1 (taps b = 0,1), -2 -> site 2 (b = 0); W -> site 2
+                        // (b = 3,4), W+1 -> site 1 (b = 4)
+                        auto cols = [&](const f2 (&row)[8]) {
+                            if (lft[u]) {
+                                out[u][1] = fma2s(row[3], w5[0], fma2s(row[2], w5[1], out[u][1]));
+                                out[u][2] = fma2s(row[2], w5[0], out[u][2]);
+                                acc[0] = fma2vv(c[u][1], row[3], fma2vv(c[u][2], row[2], acc[0]));
+                                acc[1] = fma2vv(c[u][1], row[2], acc[1]);
+                            }
+                            if (rgt[u]) {
+                                out[u][2] = fma2s(row[5], w5[3], fma2s(row[4], w5[4], out[u][2]));
+                                out[u][1] = fma2s(row[5], w5[4], out[u][1]);
+                                acc[3] = fma2vv(c[u][2], row[5], acc[3]);
+                                acc[4] = fma2vv(c[u][2], row[4], fma2vv(c[u][1], row[5], acc[4]));
+                            }
+                        };
+                        auto full = [&](int d) {                        // window row d = gY2 row q.y - 2 + d, columns q.x - 2 .. q.x + 5
+                            f2 row[8];
+                            ld8<PN>(PG, (ir[u] + 2 + d) * PN + 2 * (ig[u] + 2), row);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int bb = 0; bb < 5; ++bb) out[u][j] = fma2s(row[j + 4 - bb], w5[bb], out[u][j]);
+#pragma unroll
+                            for (int bb = 0; bb < 5; ++bb)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) acc[bb] = fma2vv(c[u][j], row[j + 4 - bb], acc[bb]);
+                            if (lft[u] | rgt[u]) cols(row);
+                        };
+                        full(4 - A);
+                        // folded pad rows that act through tap row A (isp_bwd3.cuh B5): pad row -1 -> row 1, -2 -> row 2,
+                        // H -> row H-2, H+1 -> row H-3
+                        if (A == 0 && rt[u] == 2) full(0);
+                        if (A == 0 && rt[u] == 1) full(2);
+                        if (A == 1 && rt[u] == 1) full(1);
+                        if (A == 3 && rt[u] == 3) full(3);
+                        if (A == 4 && rt[u] == 3) full(2);
+                        if (A == 4 && rt[u] == 4) full(4);
+                    }
+                    {
+                        float wa[5];
+#pragma unroll
+                        for (int bb = 0; bb < 5; ++bb) wa[bb] = acc[bb].x + acc[bb].y;
+                        R2L_PARK_STORE(5, kB5Wg + 5 * A, wa)
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < NI5; ++u) {
+                    if (!inside[u]) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) out[u][j] = mk2(0.f, 0.f);
+                    }
+                    st4<PN>(GY1, (ir[u] + 2) * PN + 2 * (ig[u] + 2), out[u][0], out[u][1], out[u][2], out[u][3]);
+                }
+            }
+            // -- halo ring: single runs, no statistic
+            for (int item = TH * G + tid; item < Cfg::G1H * GG; item += NT) {
+                int r, g;
+                region_item<TH, G, 2>(item, r, g);
+                const int qy = ty0 + r, qx = tx0 + 4 * g;
+                const bool inside = qy >= 0 && qy < H && qx >= 0 && qx < W;
+                f2 out[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
+                if (inside) {
+                    const bool lft = qx == 0, rgt = qx + 4 == W;
+                    const int rt = qy == 1 ? 1 : (qy == 2 ? 2 : (qy == H - 2 ? 3 : (qy == H - 3 ? 4 : 0)));
+                    auto full = [&](int d, int A) {
+                        f2 row[8];
+                        ld8<PN>(PG, (r + 2 + d) * PN + 2 * (g + 2), row);
+                        float w5[5];
+#pragma unroll
+                        for (int bb = 0; bb < 5; ++bb) w5[bb] = wg[A * 5 + bb];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int bb = 0; bb < 5; ++bb) out[j] = fma2s(row[j + 4 - bb], w5[bb], out[j]);
+                        if (lft) {
+                            out[1] = fma2s(row[3], w5[0], fma2s(row[2], w5[1], out[1]));
+                            out[2] = fma2s(row[2], w5[0], out[2]);
+                        }
+                        if (rgt) {
+                            out[2] = fma2s(row[5], w5[3], fma2s(row[4], w5[4], out[2]));
+                            out[1] = fma2s(row[5], w5[4], out[1]);
+                        }
+                    };
+#pragma unroll
+                    for (int d = 0; d < 5; ++d) full(d, 4 - d);
+                    if (rt == 2) full(0, 0);
+                    if (rt == 1) { full(1, 1); full(2, 0); }
+                    if (rt == 3) { full(2, 4); full(3, 3); }
+                    if (rt == 4) full(4, 4);
+                }
+                st4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), out[0], out[1], out[2], out[3]);
+            }
+        } }
+        R2L_SYNC();
+
+        // ---- B6: gY0 = corr^T(gY1, Ws) (zero pad) on rows -1..TH, runs -1..G, zero outside the image; Ws statistic ----
+        { R2L_FOR_THREADS(NT) {
+            float ws[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) ws[t] = T->Ws[t];
+            f2 ws2[9];                                                 // packed (image A, image B) dWs sums
+            {
+                float wa[9];
+                R2L_PARK_LOAD(9, kB5Ws, wa)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) ws2[t] = mk2(wa[t], 0.f);
+            }
+            auto b6 = [&](auto NRc, int r, int g, bool owned) {
+                constexpr int NR = decltype(NRc)::value;
+                const int qy = ty0 + r;
+                f2 c[NR][4], out[NR][4];
+#pragma unroll
+                for (int u = 0; u < NR; ++u) {
+                    const int qx = tx0 + 4 * (g + u * (G / 2));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { out[u][j] = mk2(0.f, 0.f); c[u][j] = mk2(0.f, 0.f); }
+                    if (owned && qy < H && qx < W) ld_luma4(y0pair + ((size_t)qy * W + qx) * 2, c[u]);
+                }
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    f2 row[NR][6];                                      // gY1 row q.y - 1 + d, columns q.x - 1 .. q.x + 4
+#pragma unroll
+                    for (int u = 0; u < NR; ++u) ld6<PN>(GY1, (r + 1 + d) * PN + 2 * (g + u * (G / 2) + 2), row[u]);
+                    const int aa = 2 - d;
+#pragma unroll
+                    for (int u = 0; u < NR; ++u)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int bb = 0; bb < 3; ++bb) out[u][j] = fma2s(row[u][j + 2 - bb], ws[aa * 3 + bb], out[u][j]);
+                    if (owned) {
+#pragma unroll
+                        for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+                            for (int u = 0; u < NR; ++u)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    ws2[aa * 3 + bb] = fma2vv(c[u][j], row[u][j + 2 - bb], ws2[aa * 3 + bb]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < NR; ++u) {
+                    const int qx = tx0 + 4 * (g + u * (G / 2));
+                    if (qy < 0 || qy >= H || qx < 0 || qx >= W) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) out[u][j] = mk2(0.f, 0.f);
+                    }
+                    st4<PN>(PG, (r + 4) * PN + 2 * (g + u * (G / 2) + 2), out[u][0], out[u][1], out[u][2], out[u][3]);
+                }
+            };
+            for (int item = tid; item < TH * (G / 2); item += NT)       // owned rectangle: paired items
+                b6(std::integral_constant<int, 2>(), item / (G / 2), item % (G / 2), true);
+            for (int item = TH * G + tid; item < (TH + 2) * GG; item += NT) {      // halo ring, single runs
+                int r, g;
+                region_item<TH, G, 1>(item, r, g);
+                b6(std::integral_constant<int, 1>(), r, g, false);
+            }
+            {
+                float wa[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) wa[t] = ws2[t].x + ws2[t].y;
+                R2L_PARK_STORE(9, kB5Ws, wa)
+            }
+        } }
+        R2L_SYNC();
+
+        // ---- B7: Q' / P statistics and g_raw from the (gY0, gU, gV) windows; border rules as in isp_bwd3.cuh B7 ----
+        // One gradient plane k and one TAP ROW A of the 3x3 at a time over the thread's items (rows of its CFA row phase
+        // x runs): only that pass's six packed (image A, image B) Q' sums are live, a tap costs one FFMA2 for the
+        // statistic and one for g_raw, and the items keep their raw centres and g_raw sums across the nine passes.
+        // Tap row A reaches window row 2 - A; the reflect-1 pad row above row 1 (below row H-2) acts through tap row 0
+        // (2) on window row 0 (2), pad columns through taps b = 0 / 2 of the first / last run.
+        { R2L_FOR_THREADS(NT) {
+            const int rp = (tid >> 5) & 1, slot = ((tid >> 6) << 5) | (tid & 31);
+            constexpr int NI = (TH / 2) * G / HALF;
+            f2 c[NI][4], graw[NI][4];
+            int ir[NI], ig[NI];
+            bool live[NI], f_top[NI], f_bot[NI], f_lft[NI], f_rgt[NI];
+#pragma unroll
+            for (int u = 0; u < NI; ++u) {
+                const int i = slot + u * HALF;
+                const int ri = i / G, g = i - ri * G;
+                const int r = rp + 2 * ri;
+                const int qy = ty0 + r, qx = tx0 + 4 * g;
+                ir[u] = r; ig[u] = g;
+                live[u] = qy < H && qx < W;                             // partial tiles: nothing there (all gradients zero)
+                f_top[u] = qy == 1; f_bot[u] = qy == H - 2; f_lft[u] = qx == 0; f_rgt[u] = qx + 4 == W;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { c[u][j] = mk2(0.f, 0.f); graw[u][j] = mk2(0.f, 0.f); }
+                if (live[u]) {                                          // raw centres of the 4 sites, packed once
+                    if (sizeof(RawT) == 4) {
+                        const f4 xa = ld_stream4(reinterpret_cast<const float*>(imgA) + (size_t)qy * W + qx);
+                        const f4 xb = ld_stream4(reinterpret_cast<const float*>(imgB) + (size_t)qy * W + qx);
+                        c[u][0] = pack2(xa.x, xb.x); c[u][1] = pack2(xa.y, xb.y); c[u][2] = pack2(xa.z, xb.z); c[u][3] = pack2(xa.w, xb.w);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            c[u][j] = pack2(RawLoad<RawT>::get(imgA + (size_t)qy * W + qx + j, a.denom),
+                                            RawLoad<RawT>::get(imgB + (size_t)qy * W + qx + j, a.denom));
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const f2* pl = k == 0 ? PG : (k == 1 ? PU : PV);
+                const volatile float* awq = &T->AWq[2 * rp][k][0];      // [col phase * 27 + tap], read next to their use
+#pragma unroll
+                for (int A = 0; A < 3; ++A) {
+                    constexpr int NP = 8;                               // 6 Q' sums [col phase][b], then (A == 1 only) 2 P sums
+                    f2 acc[2][3], p2[2];
+                    {
+                        float qa[NP];
+                        if (A == 1) { R2L_PARK_LOAD(6, kB5Q + kB5QStride * k + 6 * A, qa) R2L_PARK_LOAD(2, kB5Q + kB5QStride * k + 18, qa + 6) }
+                        else { R2L_PARK_LOAD(6, kB5Q + kB5QStride * k + 6 * A, qa) qa[6] = qa[7] = 0.f; }
+#pragma unroll
+                        for (int cp = 0; cp < 2; ++cp) {
+#pragma unroll
+                            for (int bb = 0; bb < 3; ++bb) acc[cp][bb] = mk2(qa[cp * 3 + bb], 0.f);
+                            p2[cp] = mk2(qa[6 + cp], 0.f);
+                        }
+                    }
+                    float w[2][3];
+#pragma unroll
+                    for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+                        for (int bb = 0; bb < 3; ++bb) w[cp][bb] = awq[cp * 27 + A * 3 + bb];
+#pragma unroll
+                    for (int u = 0; u < NI; ++u) {
+                        if (!live[u]) continue;
+                        auto full = [&](int d, bool centre) {           // window row d = g_yuv[k] row q.y - 1 + d, columns q.x - 1 .. q.x + 4
+                            f2 row[6];
+                            ld6<PN>(pl, (ir[u] + 3 + d) * PN + 2 * (ig[u] + 2), row);
+#pragma unroll
+                            for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const f2 t = row[j + 2 - bb];                               // g_yuv[k](q - (a-1, b-1))
+                                    acc[j & 1][bb] = fma2vv(c[u][j], t, acc[j & 1][bb]);
+                                    if (Cfg::GRAW) graw[u][j] = fma2s(t, w[j & 1][bb], graw[u][j]);
+                                }
+                            if (centre) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) p2[j & 1] = add2v(p2[j & 1], row[j + 1]);
+                            }
+                            if (f_lft[u]) {                             // pad column -1 -> site 1, tap b = 0
+                                acc[1][0] = fma2vv(c[u][1], row[1], acc[1][0]);
+                                if (Cfg::GRAW) graw[u][1] = fma2s(row[1], w[1][0], graw[u][1]);
+                            }
+                            if (f_rgt[u]) {                             // pad column W -> site 2, tap b = 2
+                                acc[0][2] = fma2vv(c[u][2], row[4], acc[0][2]);
+                                if (Cfg::GRAW) graw[u][2] = fma2s(row[4], w[0][2], graw[u][2]);
+                            }
+                        };
+                        full(2 - A, A == 1);
+                        if (A == 0 && f_top[u]) full(0, false);
+                        if (A == 2 && f_bot[u]) full(2, false);
+                    }
+                    {
+                        float qa[NP];
+#pragma unroll
+                        for (int cp = 0; cp < 2; ++cp) {
+#pragma unroll
+                            for (int bb = 0; bb < 3; ++bb) qa[cp * 3 + bb] = acc[cp][bb].x + acc[cp][bb].y;
+                            qa[6 + cp] = p2[cp].x + p2[cp].y;
+                        }
+                        R2L_PARK_STORE(6, kB5Q + kB5QStride * k + 6 * A, qa)
+                        if (A == 1) { R2L_PARK_STORE(2, kB5Q + kB5QStride * k + 18, qa + 6) }
+                    }
+                }
+            }
+            if (Cfg::GRAW) {
+#pragma unroll
+                for (int u = 0; u < NI; ++u) {
+                    if (!live[u]) continue;
+                    const size_t off = (size_t)(ty0 + ir[u]) * W + tx0 + 4 * ig[u];
+                    float* pa = a.graw + (size_t)b0 * plane + off;
+                    f4 va; va.x = graw[u][0].x; va.y = graw[u][1].x; va.z = graw[u][2].x; va.w = graw[u][3].x;
+                    *reinterpret_cast<f4*>(pa) = va;
+                    if (!dup) {
+                        float* pb = a.graw + (size_t)b1 * plane + off;
+                        f4 vb; vb.x = graw[u][0].y; vb.y = graw[u][1].y; vb.z = graw[u][2].y; vb.w = graw[u][3].y;
+                        *reinterpret_cast<f4*>(pb) = vb;
+                    }
+                }
+            }
+        } }
+        R2L_SYNC();   // planes are rewritten by the next tile
+    }
+
+    // ---- CTA reduction of the per-thread statistics into the kStat* layout (deterministic, fixed order), as in
+    // isp_bwd3.cuh; the sums come back from tensor memory ----------------------------------------------------------
+    float* part = a.partials + (size_t)cta * kStatPitch;
+    constexpr int NW = NT / 32;
+    constexpr int RP = kBwd5AccFloats + 1;
+    float* red = reinterpret_cast<float*>(PU);                       // [NW][RP]
+#ifdef R2L_HOST_EMU
+    for (int w = 0; w < NW; ++w)
+        for (int i = 0; i < kBwd5AccFloats; ++i) {
+            float sum = 0.f;
+            for (int l = 0; l < 32; ++l) sum += accs[w * 32 + l].sums[i];
+            red[w * RP + i] = sum;
+        }
+#else
+    {
+        static_assert(kBwd5AccFloats == 96, "three groups of 32 running sums");
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int grp = 0; grp < 3; ++grp) {
+            float v[32];
+            __syncwarp();
+            tmem::load<16>(tacc + grp * 32, v);
+            tmem::load<16>(tacc + grp * 32 + 16, v + 16);
+            tmem::wait_ld();
+            red[warp * RP + grp * 32 + lane] = warp_transpose_sum32(v);
+        }
+        tmem::fence_before_sync();
+    }
+#endif
+    R2L_SYNC();
+#ifndef R2L_HOST_EMU
+    if (threadIdx.x < 32) tmem::dealloc<Cfg::kTmemCols>(tmem_base);  // every warp has read its sums back
+#endif
+    { R2L_FOR_THREADS(NT) {
+        for (int s = tid; s < kNumStats; s += NT) {
+            float sum = 0.f;
+            if (s == kStatGamma) {
+                for (int w = 0; w < NW; ++w) sum += red[w * RP] + red[w * RP + 1];
+            } else if (s < kStatQ) {                                 // Wg, Ws: same slot in every thread
+                for (int w = 0; w < NW; ++w) sum += red[w * RP + s + 1];
+            } else {
+                int k, parp, tt = 0;
+                bool is_q;
+                if (s < kStatP) { const int rI = s - kStatQ; k = rI / 36; parp = (rI - 36 * k) / 9; tt = rI - 36 * k - 9 * parp; is_q = true; }
+                else { const int rI = s - kStatP; k = rI / 4; parp = rI - 4 * k; is_q = false; }
+                // Q[k][par(p)][t] = Q'[par(q) = par_tap(par(p), t)][k][t];  P is already p-indexed (p = q)
+                const int parq = is_q ? par_tap(parp, tt) : parp;
+                const int rpq = parq >> 1, cpq = parq & 1;
+                const int off = kB5Q + kB5QStride * k + (is_q ? 6 * (tt / 3) + 3 * cpq + tt % 3 : 18 + cpq);
+                for (int w = rpq; w < NW; w += 2) sum += red[w * RP + off];      // warps of row phase rpq
+            }
+            part[s] = sum;
+        }
+    } }
+#ifndef R2L_HOST_EMU
+    if (a.ticket) {
+        __shared__ unsigned last_flag;
+        __threadfence();                                             // this CTA's partial sums are visible device-wide ...
+        __syncthreads();
+        if (threadIdx.x == 0) last_flag = atomicAdd(a.ticket, 1u) == (unsigned)n_cta - 1u;   // ... before its ticket is
+        __syncthreads();
+        if (last_flag) {
+            __threadfence();
+            static_assert((size_t)(NT / 32 + 1) * kStatPitch * 8 + 130 * 8 <= (size_t)Cfg::kSites * 8, "finish scratch fits the planes");
+            fused_finish<NT>(T, a.partials, n_cta, a.grads, reinterpret_cast<double*>(PU));
+        }
+    }
+#endif
+}
+
+}  // namespace r2l

@@ -1,0 +1,51 @@
+// isp_bwd5_tu.cuh -- fifth-generation backward kernels + launcher for one raw element type
+#pragma once
+#include "isp_launch.h"
+#ifndef R2L_B5_MINB
+#define R2L_B5_MINB CPS
+#endif
+
+namespace r2l {
+
+template <class Cfg, typename RawT, int CPS>
+__global__ void __launch_bounds__(Cfg::NT, R2L_B5_MINB) isp_backward5_kernel(BwdArgs a, TileGrid grid) {
+    extern __shared__ __align__(128) float smem[];
+    bwd5_cta<Cfg, RawT>(blockIdx.x, gridDim.x, a, grid, smem);
+}
+
+template <class Cfg, typename RawT, int CPS>
+static int launch_backward5_t(const BwdArgs& a, cudaStream_t st, int* grid_used) {
+    const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);     // tiles of image pairs
+    int g = 0;
+    int rc = tmem_ctas_per_device(reinterpret_cast<const void*>(isp_backward5_kernel<Cfg, RawT, CPS>), Cfg::NT, Cfg::kSmemBytes,
+                                  Cfg::kTmemCols, CPS, &g);
+    if (rc != R2L_OK) return rc;
+    if (g > grid.n) g = grid.n;
+    if (g > kMaxCtas) g = kMaxCtas;
+    if (rc != R2L_OK) return rc;
+    if (a.ticket) {
+        cudaError_t e0 = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned), st);
+        if (e0 != cudaSuccess) return cuda_fail(e0);
+    }
+    isp_backward5_kernel<Cfg, RawT, CPS><<<g, Cfg::NT, Cfg::kSmemBytes, st>>>(a, grid);
+    if (grid_used) *grid_used = g;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? R2L_OK : cuda_fail(e);
+}
+
+// kNotServed when the shape or an alignment rule sends the call to an older generation
+template <typename RawT>
+static int launch_backward5_impl(const BwdArgs& a, cudaStream_t st, int* grid_used) {
+    if (!a.out || !a.luma || !bwd5_shape_ok(a.H, a.W)) return kNotServed;
+    if (!aligned(a.gout, 16) || !aligned(a.graw, 16) || !aligned(a.additive, 16) || !aligned(a.out, 16) ||
+        !aligned(a.luma, 16) || !aligned(a.raw, 4 * sizeof(RawT)))
+        return kNotServed;                                                          // 128-bit rows
+    const bool tail = a.gtail != nullptr;
+    constexpr int CPS = kBwd5CtasPerSm;
+    if (a.graw) return tail ? launch_backward5_t<Bwd5<true, true>, RawT, CPS>(a, st, grid_used)
+                            : launch_backward5_t<Bwd5<true, false>, RawT, CPS>(a, st, grid_used);
+    return tail ? launch_backward5_t<Bwd5<false, true>, RawT, CPS>(a, st, grid_used)
+                : launch_backward5_t<Bwd5<false, false>, RawT, CPS>(a, st, grid_used);
+}
+
+}  // namespace r2l

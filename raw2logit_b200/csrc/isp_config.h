@@ -5,6 +5,7 @@
 #include "isp_bwd3.cuh"
 #include "isp_fwd3.cuh"
 #include "isp_bwd4.cuh"
+#include "isp_bwd5.cuh"
 
 namespace r2l {
 using FwdDefault = FwdCfg<32, 64, 256>;          // v1 (scalar) -- kept for the emulation cross-check only
@@ -17,5 +18,8 @@ template <bool GRAW, bool TAIL, bool OUT = false> using Bwd3 = Bwd3Cfg<32, 64, 2
 // v4: forward output + saved Y0/Y1 planes, nothing recomputed, two CTAs per SM; <TH, TW, NT, GRAW, TAIL>
 template <bool GRAW, bool TAIL> using Bwd4 = Bwd4Cfg<32, 64, 128, GRAW, TAIL>;
 constexpr int kBwd4CtasPerSm = 2;
+// v5: v4 with the running sums parked in tensor memory, 256 threads x 2 CTAs per SM at <= 128 registers
+template <bool GRAW, bool TAIL> using Bwd5 = Bwd5Cfg<32, 64, 256, GRAW, TAIL>;
+constexpr int kBwd5CtasPerSm = 2;
 constexpr int kMaxCtas = 2048;          // upper bound on persistent CTAs == rows of the statistics workspace
 }  // namespace r2l

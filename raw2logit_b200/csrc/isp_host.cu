@@ -289,6 +289,43 @@ int cached_ctas_per_device(const void* kernel, int threads, size_t smem, int* ou
     return R2L_OK;
 }
 
+int tmem_ctas_per_device(const void* kernel, int threads, size_t smem, int tmem_cols, int want_per_sm, int* out) {
+    struct Entry { const void* kernel; int dev; int ctas; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (const Entry& en : cache)
+            if (en.kernel == kernel && en.dev == dev) { *out = en.ctas; return R2L_OK; }
+    }
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e);
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return cuda_fail(e);
+    int sms = 0, regs_sm = 0, smem_sm = 0, smem_reserved = 0;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev)) != cudaSuccess)
+        return cuda_fail(e);
+    const int warps = (threads + 31) / 32;
+    const int regs_cta = warps * ((fa.numRegs * 32 + 255) / 256 * 256);                // per-warp allocation unit: 256
+    const size_t smem_cta = (smem + fa.sharedSizeBytes + (size_t)smem_reserved + 127) / 128 * 128;
+    int per_sm = want_per_sm;
+    if (regs_cta > 0 && regs_sm / regs_cta < per_sm) per_sm = regs_sm / regs_cta;
+    if ((int)((size_t)smem_sm / smem_cta) < per_sm) per_sm = (int)((size_t)smem_sm / smem_cta);
+    if (tmem_cols > 0 && 512 / tmem_cols < per_sm) per_sm = 512 / tmem_cols;
+    if (per_sm < 1) return R2L_ERR_BAD_ARGUMENT;
+    std::lock_guard<std::mutex> lock(mu);
+    cache.push_back({kernel, dev, sms * per_sm});
+    *out = sms * per_sm;
+    return R2L_OK;
+}
+
 static Params to_params(const r2l_isp_params* p) {
     Params q;
     q.black_level = p->black_level; q.white_balance = p->white_balance; q.colour_correction = p->colour_correction;
@@ -375,11 +412,15 @@ static int launch_backward_any(const BwdArgs& a, int raw_dtype, float* grads, cu
     int rc = kNotServed;
     const char* force = getenv("R2L_ISP_FORCE_GENERIC");        // debugging knob
     if (!(force && force[0] == '1')) {
-        if (a.out && a.luma) {                                  // fourth generation: nothing recomputed, fused finish
+        if (a.out && a.luma) {                                  // fourth / fifth generation: nothing recomputed, fused finish
             BwdArgs a4 = a;
             a4.grads = grads;
             a4.ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.partials) + kTicketOffset);
-            rc = raw_dtype == R2L_F32 ? launch_backward4_f32(a4, st, &g) : launch_backward4_u16(a4, st, &g);
+            const char* gen = getenv("R2L_ISP_BWD_GEN");            // debugging knob: 4 = registers-only predecessor
+            if (gen && gen[0] == '4')
+                rc = raw_dtype == R2L_F32 ? launch_backward4_f32(a4, st, &g) : launch_backward4_u16(a4, st, &g);
+            else
+                rc = raw_dtype == R2L_F32 ? launch_backward5_f32(a4, st, &g) : launch_backward5_u16(a4, st, &g);
             if (rc == R2L_OK) return rc;
         }
         if (rc == kNotServed) rc = raw_dtype == R2L_F32 ? launch_backward3_f32(a, st, &g) : launch_backward3_u16(a, st, &g);

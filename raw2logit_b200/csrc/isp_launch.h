@@ -17,6 +17,12 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 // persistent grid: one wave of resident CTAs (or fewer when the job is small).  The occupancy query and the
 // dynamic-shared-memory opt-in are done once per (kernel, device) and remembered (isp_host.cu).
 int cached_ctas_per_device(const void* kernel, int threads, size_t smem, int* out);   // fills *out, returns R2L_* code
+// The same for a kernel that allocates tensor memory.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every
+// kernel that contains tcgen05.alloc, although the hardware co-schedules CTAs as long as their column allocations fit
+// the SM's 512 (profiles/microbench/tmem_occupancy.cu), so the limit is taken from the kernel's own resource use:
+// registers, shared memory, TMEM columns and the CTAs per SM it was compiled for (want_per_sm).
+int tmem_ctas_per_device(const void* kernel, int threads, size_t smem, int tmem_cols, int want_per_sm, int* out);
+
 template <typename K>
 static int persistent_grid(K kernel, int threads, size_t smem, int n_tiles, int* grid_out) {
     int g = 0;
@@ -41,6 +47,9 @@ int launch_backward3_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
 // fourth-generation backward (forward output + saved luma planes, fused finish when a.ticket is set)
 int launch_backward4_f32(const BwdArgs& a, cudaStream_t st, int* grid_used);
 int launch_backward4_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
+// fifth-generation backward (the fourth with its running sums in tensor memory)
+int launch_backward5_f32(const BwdArgs& a, cudaStream_t st, int* grid_used);
+int launch_backward5_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
 // generic scalar kernels: any shape, any alignment
 int launch_backward_generic(const BwdArgs& a, int raw_dtype, cudaStream_t st, int* grid_used);
 constexpr int kNotServed = 1;

@@ -14,6 +14,7 @@ DEPS = [SRC, os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_core.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd3.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_fwd3.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd4.cuh"),
+        os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd5.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_config.h"), os.path.join(ROOT, "include", "r2l_isp.h")]
 
 PARAM_FIELDS = ["black_level", "white_balance", "colour_correction", "gamma_correct", "debayer.weight",

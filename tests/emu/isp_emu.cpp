@@ -51,7 +51,18 @@ static void run_backward(const BwdArgs& a, int n_cta, float* grads, int version)
         const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
         std::vector<float> smem(Cfg::kSmemFloats);
         for (int cta = 0; cta < n_cta; ++cta) bwd_cta<Cfg, RawT>(cta, n_cta, a, grid, smem.data());
-    } else if (version == 4 && a.out && a.luma && bwd4_shape_ok(a.H, a.W)) {     // same dispatch rule as the CUDA launcher
+    } else if (version == 5 && a.out && a.luma && bwd5_shape_ok(a.H, a.W)) {     // same dispatch rule as the CUDA launcher
+        auto go5 = [&](auto cfg) {
+            using C5 = decltype(cfg);
+            const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, C5::TH, C5::TW);
+            std::vector<float> smem(C5::kSmemBytes / 4 + 4);
+            float* base = smem.data();
+            while (reinterpret_cast<uintptr_t>(base) % 16) ++base;
+            for (int cta = 0; cta < n_cta; ++cta) bwd5_cta<C5, RawT>(cta, n_cta, a, grid, base);
+        };
+        if (a.gtail) go5(Bwd5<Cfg::GRAW, true>());
+        else go5(Bwd5<Cfg::GRAW, false>());
+    } else if (version == 4 && a.out && a.luma && bwd4_shape_ok(a.H, a.W)) {
         auto go4 = [&](auto cfg) {
             using C4 = decltype(cfg);
             const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, C4::TH, C4::TW);
@@ -62,7 +73,7 @@ static void run_backward(const BwdArgs& a, int n_cta, float* grads, int version)
         };
         if (a.gtail) go4(Bwd4<Cfg::GRAW, true>());
         else go4(Bwd4<Cfg::GRAW, false>());
-    } else if (version == 3 || version == 4) {
+    } else if (version == 3 || version == 4 || version == 5) {
         if (!bwd3_shape_ok(a.H, a.W, Cfg::TH, Cfg::TW)) {           // same dispatch rule as the CUDA launcher
             run_backward<Cfg, RawT>(a, n_cta, grads, 1);
             return;

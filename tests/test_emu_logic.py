@@ -246,10 +246,12 @@ V4_SHAPES = [((3, 72, 136), 3, True), ((2, 64, 128), 3, False), ((1, 40, 72), 2,
              ((3, 96, 200), 5, True)]
 
 
+@pytest.mark.parametrize("gen", [4, 5])
 @pytest.mark.parametrize("shape,n_cta,need_raw", V4_SHAPES)
-def test_saved_luma_planes_and_v4_backward(shape, n_cta, need_raw):
+def test_saved_luma_planes_and_v4_backward(shape, n_cta, need_raw, gen):
     """The forward's saved luma planes equal the oracle's Y0 / Y1 (pair-interleaved layout, odd batches duplicate the
-    last image), and the fourth-generation backward fed with them matches the fp64 oracle and the third generation."""
+    last image), and the fourth / fifth-generation backward fed with them matches the fp64 oracle and the third
+    generation."""
     raw = syn.smooth_scene(*shape, "drone", seed=sum(shape) + 2)
     st = syn.perturbed_state(isp_oracle.default_state(syn.CAMERA_PRESETS["drone"]))
     b, h, w = shape
@@ -264,7 +266,7 @@ def test_saved_luma_planes_and_v4_backward(shape, n_cta, need_raw):
         assert np.array_equal(luma[:, -1, :, :, 1], luma[:, -1, :, :, 0])
     want, grads = isp_oracle.forward_backward(raw, st, grad_out="ramp", dtype=torch.float64)
     g = isp_oracle.cotangent(tuple(want.shape), "ramp").numpy()
-    got = emu.backward(raw.numpy(), st, g, n_cta=n_cta, need_raw_grad=need_raw, out=out, luma=luma, version=4)
+    got = emu.backward(raw.numpy(), st, g, n_cta=n_cta, need_raw_grad=need_raw, out=out, luma=luma, version=gen)
     ref = emu.backward(raw.numpy(), st, g, n_cta=n_cta, need_raw_grad=need_raw, out=out, version=3)
     for k, v in got.items():
         r64 = grads[k].numpy()
@@ -275,8 +277,9 @@ def test_saved_luma_planes_and_v4_backward(shape, n_cta, need_raw):
 
 @pytest.mark.parametrize("name", ["bn_train", "bn_train_additive", "noise_g2_pert", "car_crop", "impulses", "drone_g1_pert",
                                   "micro_g1_pert"])
-def test_v4_backward_golden_cases(name):
-    """Fourth generation on the golden cases (clip-heavy inputs, BatchNorm / additive tails, impulses at every CFA
+@pytest.mark.parametrize("gen", [4, 5])
+def test_v4_backward_golden_cases(name, gen):
+    """Fourth / fifth generation on the golden cases (clip-heavy inputs, BatchNorm / additive tails, impulses at every CFA
     phase and border)."""
     c = GoldenCase(name)
     cot = "ramp"
@@ -291,7 +294,7 @@ def test_v4_backward_golden_cases(name):
         tail = None
         if add is not None:
             tail = np.asarray([1, 1, 1, 0, 0, 0, 0, 0, 0, 1, 1, 1, 0, 0, 0], dtype=np.float32)
-        got = emu.backward(c.raw.numpy(), c.state, g, out=out, luma=luma, version=4, grad_tail=tail, additive=add)
+        got = emu.backward(c.raw.numpy(), c.state, g, out=out, luma=luma, version=gen, grad_tail=tail, additive=add)
     else:
         add = None if c.additive is None else c.additive
         emu.forward(c.raw.numpy(), c.state, additive=None if add is None else add.numpy()[0], luma=luma)
@@ -304,7 +307,7 @@ def test_v4_backward_golden_cases(name):
         tail = torch.cat([inv, gt.mean(dim=(0, 2, 3)), (gt * y).mean(dim=(0, 2, 3)), inv, -mean * inv]).float().numpy()
         addn = None if add is None else add.numpy()[0]
         got = emu.backward(c.raw.numpy(), c.state, gt.float().numpy(), grad_tail=tail, additive=addn,
-                           out=y.float().numpy(), luma=luma, version=4)
+                           out=y.float().numpy(), luma=luma, version=gen)
     for k, v in got.items():
         r64 = c.f64[f"grad.{cot}.{k}"]
         assert maxabs(v.reshape(r64.shape), r64) <= 1e-4, (name, k)
