@@ -32,26 +32,19 @@ template <int TH_, int TW_, int NT_, bool GRAW_, bool TAIL_> struct Bwd5Cfg : Bw
 
 inline bool bwd5_shape_ok(int H, int W) { return bwd4_shape_ok(H, W); }
 
-// (x, y) -> one aligned register pair, materialised once (a plain make_float2 of values from two different loads is
-// re-packed with two MOVs at every FFMA2 that uses it when registers are tight)
-R2L_HD f2 pack2(float x, float y) {
-#ifdef R2L_HOST_EMU
-    return mk2(x, y);
-#else
-    unsigned long long r;
-    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
-    f2 o;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
-    return o;
-#endif
-}
+// (x, y) -> one aligned register pair that stays one: a plain make_float2 of values from two different loads is
+// re-packed with two MOVs at every FFMA2 that uses it when registers are tight (profiles/r01_v5_summary.md), and
+// ptxas folds a mov.b64 pack / unpack away; a packed multiply by a run-time 1.0 produces the pair as an FMUL2 result.
+R2L_HD f2 pack2(float x, float y, float one) { return mul2s(mk2(x, y), one); }
 
 // a phase's view of its running sums: load at phase start, store at phase end
 #ifdef R2L_HOST_EMU
+#define R2L_ANY(x) (x)
 #define R2L_PARK_LOAD(N, col, v)  { const float* s_ = accs[tid].sums + (col); for (int i_ = 0; i_ < (N); ++i_) (v)[i_] = s_[i_]; }
 #define R2L_PARK_STORE(N, col, v) { float* s_ = accs[tid].sums + (col); for (int i_ = 0; i_ < (N); ++i_) s_[i_] = (v)[i_]; }
 struct Bwd5Acc { float sums[kBwd5AccFloats]; };
 #else
+#define R2L_ANY(x) (__any_sync(0xffffffffu, (x)) != 0)
 #define R2L_PARK_LOAD(N, col, v)  { __syncwarp(); tmem::load<N>(tacc + (col), v); tmem::wait_ld(); }
 #define R2L_PARK_STORE(N, col, v) { __syncwarp(); tmem::store<N>(tacc + (col), v); tmem::wait_st(); }
 #endif
@@ -254,65 +247,82 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     for (int j = 0; j < 4; ++j) { out[u][j] = mk2(0.f, 0.f); c[u][j] = mk2(0.f, 0.f); }
                     if (inside[u]) ld_luma4(y1pair + ((size_t)qy * W + qx) * 2, c[u]);
                 }
+                // Pad columns (reflect-2 of the sharpened plane: -1 -> site 1, -2 -> site 2, W -> site W-2, W+1 -> W-3) are
+                // realised on the data, so the loop is straight-line code: the adjoint of the first / last run of the image
+                // uses per-site weights for its sites 1 and 2 (tap b gains the tap that reaches the same gradient through
+                // the pad), the statistic adds the pad sites' products with centres masked by L / R (zero elsewhere).
+                // Items outside the image (partial tiles) run with zero centres and are zeroed when stored.
+                float Lf[NI5], Rf[NI5];
+                f2 cl1[NI5], cl2[NI5], cr1[NI5], cr2[NI5];
+                bool padrows = false;
 #pragma unroll
+                for (int u = 0; u < NI5; ++u) {
+                    Lf[u] = (inside[u] && lft[u]) ? 1.f : 0.f;
+                    Rf[u] = (inside[u] && rgt[u]) ? 1.f : 0.f;
+                    cl1[u] = mul2s(c[u][1], Lf[u]); cl2[u] = mul2s(c[u][2], Lf[u]);
+                    cr1[u] = mul2s(c[u][1], Rf[u]); cr2[u] = mul2s(c[u][2], Rf[u]);
+                    if (!inside[u]) rt[u] = 0;
+                    padrows |= rt[u] != 0;
+                }
+                // products of window row d (gY2 row q.y - 2 + d, columns q.x - 2 .. q.x + 5) with the tap row in w5 / acc
+                auto full = [&](int u, int d, const float (&w5)[5], f2 (&acc)[5]) {
+                    // sites 1 and 2: out[1] also receives row[3] w0 + row[2] w1 (L) and row[5] w4 (R), out[2] receives
+                    // row[2] w0 (L) and row[5] w3 + row[4] w4 (R); row[i] is column q.x - 2 + i
+                    const float w1_0 = fmaf_(Rf[u], w5[4], w5[0]), w1_2 = fmaf_(Lf[u], w5[0], w5[2]), w1_3 = fmaf_(Lf[u], w5[1], w5[3]);
+                    const float w2_1 = fmaf_(Rf[u], w5[3], w5[1]), w2_2 = fmaf_(Rf[u], w5[4], w5[2]), w2_4 = fmaf_(Lf[u], w5[0], w5[4]);
+                    f2 row[8];
+                    ld8<PN>(PG, (ir[u] + 2 + d) * PN + 2 * (ig[u] + 2), row);
+#pragma unroll
+                    for (int bb = 0; bb < 5; ++bb) {
+                        out[u][0] = fma2s(row[4 - bb], w5[bb], out[u][0]);
+                        out[u][3] = fma2s(row[7 - bb], w5[bb], out[u][3]);
+                    }
+                    out[u][1] = fma2s(row[5], w1_0, fma2s(row[4], w5[1], fma2s(row[3], w1_2, fma2s(row[2], w1_3, fma2s(row[1], w5[4], out[u][1])))));
+                    out[u][2] = fma2s(row[6], w5[0], fma2s(row[5], w2_1, fma2s(row[4], w2_2, fma2s(row[3], w5[3], fma2s(row[2], w2_4, out[u][2])))));
+#pragma unroll
+                    for (int bb = 0; bb < 5; ++bb)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[bb] = fma2vv(c[u][j], row[j + 4 - bb], acc[bb]);
+                    // pad sites' share of dWg: Y1pad(-1) = Y1(1), Y1pad(-2) = Y1(2), Y1pad(W) = Y1(W-2), Y1pad(W+1) = Y1(W-3)
+                    acc[0] = fma2vv(cl1[u], row[3], fma2vv(cl2[u], row[2], acc[0]));
+                    acc[1] = fma2vv(cl1[u], row[2], acc[1]);
+                    acc[3] = fma2vv(cr2[u], row[5], acc[3]);
+                    acc[4] = fma2vv(cr2[u], row[4], fma2vv(cr1[u], row[5], acc[4]));
+                };
+#pragma unroll 1
                 for (int A = 0; A < 5; ++A) {
                     f2 acc[5];
-                    {
-                        float wa[5];
+                    float wa[5], w5[5];
+                    R2L_PARK_LOAD(5, kB5Wg + 5 * A, wa)
+#pragma unroll
+                    for (int bb = 0; bb < 5; ++bb) { acc[bb] = mk2(0.f, 0.f); w5[bb] = wg[A * 5 + bb]; }
+#pragma unroll
+                    for (int u = 0; u < NI5; ++u) full(u, 4 - A, w5, acc);
+#pragma unroll
+                    for (int bb = 0; bb < 5; ++bb) wa[bb] += acc[bb].x + acc[bb].y;
+                    R2L_PARK_STORE(5, kB5Wg + 5 * A, wa)
+                }
+                // folded pad rows (isp_bwd3.cuh B5: pad row -1 -> row 1, -2 -> row 2, H -> row H-2, H+1 -> row H-3): only
+                // warps that hold one of those four image rows come here.  Row type rt acts through tap row A on window
+                // row d: (rt 1: A 0 / d 2, A 1 / d 1), (rt 2: A 0 / d 0), (rt 3: A 3 / d 3, A 4 / d 2), (rt 4: A 4 / d 4).
+                if (R2L_ANY(padrows)) {
+#pragma unroll 1
+                    for (int A = 0; A < 5; ++A) {
+                        if (A == 2) continue;
+                        f2 acc[5];
+                        float wa[5], w5[5];
                         R2L_PARK_LOAD(5, kB5Wg + 5 * A, wa)
 #pragma unroll
-                        for (int bb = 0; bb < 5; ++bb) acc[bb] = mk2(wa[bb], 0.f);
-                    }
-                    float w5[5];
+                        for (int bb = 0; bb < 5; ++bb) { acc[bb] = mk2(0.f, 0.f); w5[bb] = wg[A * 5 + bb]; }
 #pragma unroll
-                    for (int bb = 0; bb < 5; ++bb) w5[bb] = wg[A * 5 + bb];
+                        for (int u = 0; u < NI5; ++u) {
+                            const int t = rt[u];
+                            const int d = A == 0 ? (t == 2 ? 0 : (t == 1 ? 2 : -1)) : A == 1 ? (t == 1 ? 1 : -1)
+                                        : A == 3 ? (t == 3 ? 3 : -1) : (t == 3 ? 2 : (t == 4 ? 4 : -1));
+                            if (d >= 0) full(u, d, w5, acc);
+                        }
 #pragma unroll
-                    for (int u = 0; u < NI5; ++u) {
-                        if (!inside[u]) continue;
-                        // products of one window row with tap row A: adjoint, statistic, and (first / last run of the
-                        // image) the pad columns' share: -1 -> site 1 (taps b = 0,1), -2 -> site 2 (b = 0); W -> site 2
-                        // (b = 3,4), W+1 -> site 1 (b = 4)
-                        auto cols = [&](const f2 (&row)[8]) {
-                            if (lft[u]) {
-                                out[u][1] = fma2s(row[3], w5[0], fma2s(row[2], w5[1], out[u][1]));
-                                out[u][2] = fma2s(row[2], w5[0], out[u][2]);
-                                acc[0] = fma2vv(c[u][1], row[3], fma2vv(c[u][2], row[2], acc[0]));
-                                acc[1] = fma2vv(c[u][1], row[2], acc[1]);
-                            }
-                            if (rgt[u]) {
-                                out[u][2] = fma2s(row[5], w5[3], fma2s(row[4], w5[4], out[u][2]));
-                                out[u][1] = fma2s(row[5], w5[4], out[u][1]);
-                                acc[3] = fma2vv(c[u][2], row[5], acc[3]);
-                                acc[4] = fma2vv(c[u][2], row[4], fma2vv(c[u][1], row[5], acc[4]));
-                            }
-                        };
-                        auto full = [&](int d) {                        // window row d = gY2 row q.y - 2 + d, columns q.x - 2 .. q.x + 5
-                            f2 row[8];
-                            ld8<PN>(PG, (ir[u] + 2 + d) * PN + 2 * (ig[u] + 2), row);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                                for (int bb = 0; bb < 5; ++bb) out[u][j] = fma2s(row[j + 4 - bb], w5[bb], out[u][j]);
-#pragma unroll
-                            for (int bb = 0; bb < 5; ++bb)
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) acc[bb] = fma2vv(c[u][j], row[j + 4 - bb], acc[bb]);
-                            if (lft[u] | rgt[u]) cols(row);
-                        };
-                        full(4 - A);
-                        // folded pad rows that act through tap row A (isp_bwd3.cuh B5): pad row -1 -> row 1, -2 -> row 2,
-                        // H -> row H-2, H+1 -> row H-3
-                        if (A == 0 && rt[u] == 2) full(0);
-                        if (A == 0 && rt[u] == 1) full(2);
-                        if (A == 1 && rt[u] == 1) full(1);
-                        if (A == 3 && rt[u] == 3) full(3);
-                        if (A == 4 && rt[u] == 3) full(2);
-                        if (A == 4 && rt[u] == 4) full(4);
-                    }
-                    {
-                        float wa[5];
-#pragma unroll
-                        for (int bb = 0; bb < 5; ++bb) wa[bb] = acc[bb].x + acc[bb].y;
+                        for (int bb = 0; bb < 5; ++bb) wa[bb] += acc[bb].x + acc[bb].y;
                         R2L_PARK_STORE(5, kB5Wg + 5 * A, wa)
                     }
                 }
@@ -335,26 +345,24 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 if (inside) {
                     const bool lft = qx == 0, rgt = qx + 4 == W;
                     const int rt = qy == 1 ? 1 : (qy == 2 ? 2 : (qy == H - 2 ? 3 : (qy == H - 3 ? 4 : 0)));
+                    const float Lf = lft ? 1.f : 0.f, Rf = rgt ? 1.f : 0.f;
                     auto full = [&](int d, int A) {
                         f2 row[8];
                         ld8<PN>(PG, (r + 2 + d) * PN + 2 * (g + 2), row);
                         float w5[5];
 #pragma unroll
                         for (int bb = 0; bb < 5; ++bb) w5[bb] = wg[A * 5 + bb];
+                        const float w1_0 = fmaf_(Rf, w5[4], w5[0]), w1_2 = fmaf_(Lf, w5[0], w5[2]), w1_3 = fmaf_(Lf, w5[1], w5[3]);
+                        const float w2_1 = fmaf_(Rf, w5[3], w5[1]), w2_2 = fmaf_(Rf, w5[4], w5[2]), w2_4 = fmaf_(Lf, w5[0], w5[4]);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-#pragma unroll
-                            for (int bb = 0; bb < 5; ++bb) out[j] = fma2s(row[j + 4 - bb], w5[bb], out[j]);
-                        if (lft) {
-                            out[1] = fma2s(row[3], w5[0], fma2s(row[2], w5[1], out[1]));
-                            out[2] = fma2s(row[2], w5[0], out[2]);
+                        for (int bb = 0; bb < 5; ++bb) {
+                            out[0] = fma2s(row[4 - bb], w5[bb], out[0]);
+                            out[3] = fma2s(row[7 - bb], w5[bb], out[3]);
                         }
-                        if (rgt) {
-                            out[2] = fma2s(row[5], w5[3], fma2s(row[4], w5[4], out[2]));
-                            out[1] = fma2s(row[5], w5[4], out[1]);
-                        }
+                        out[1] = fma2s(row[5], w1_0, fma2s(row[4], w5[1], fma2s(row[3], w1_2, fma2s(row[2], w1_3, fma2s(row[1], w5[4], out[1])))));
+                        out[2] = fma2s(row[6], w5[0], fma2s(row[5], w2_1, fma2s(row[4], w2_2, fma2s(row[3], w5[3], fma2s(row[2], w2_4, out[2])))));
                     };
-#pragma unroll
+#pragma unroll 1
                     for (int d = 0; d < 5; ++d) full(d, 4 - d);
                     if (rt == 2) full(0, 0);
                     if (rt == 1) { full(1, 1); full(2, 0); }
@@ -446,6 +454,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         { R2L_FOR_THREADS(NT) {
             const int rp = (tid >> 5) & 1, slot = ((tid >> 6) << 5) | (tid & 31);
             constexpr int NI = (TH / 2) * G / HALF;
+            const float one = a.B > 0 ? 1.f : 2.f;                     // 1.0 the compiler cannot see (pack2)
             f2 c[NI][4], graw[NI][4];
             int ir[NI], ig[NI];
             bool live[NI], f_top[NI], f_bot[NI], f_lft[NI], f_rgt[NI];
@@ -464,80 +473,111 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     if (sizeof(RawT) == 4) {
                         const f4 xa = ld_stream4(reinterpret_cast<const float*>(imgA) + (size_t)qy * W + qx);
                         const f4 xb = ld_stream4(reinterpret_cast<const float*>(imgB) + (size_t)qy * W + qx);
-                        c[u][0] = pack2(xa.x, xb.x); c[u][1] = pack2(xa.y, xb.y); c[u][2] = pack2(xa.z, xb.z); c[u][3] = pack2(xa.w, xb.w);
+                        c[u][0] = pack2(xa.x, xb.x, one); c[u][1] = pack2(xa.y, xb.y, one); c[u][2] = pack2(xa.z, xb.z, one); c[u][3] = pack2(xa.w, xb.w, one);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             c[u][j] = pack2(RawLoad<RawT>::get(imgA + (size_t)qy * W + qx + j, a.denom),
-                                            RawLoad<RawT>::get(imgB + (size_t)qy * W + qx + j, a.denom));
+                                            RawLoad<RawT>::get(imgB + (size_t)qy * W + qx + j, a.denom), one);
                     }
                 }
             }
+            // Pad columns (reflect-1 of the mosaic: -1 -> site 1 of the first run through tap b = 0, W -> site 2 of the last
+            // run through b = 2) on the data: g_raw uses a per-site weight for those two taps, the statistic adds the
+            // pad site's product with the centre masked by L / R.  The loop is straight-line code; items outside the
+            // image (partial tiles) have zero centres, see zero gradients and are not stored.
+            float Lf[NI], Rf[NI];
+            f2 cl1[NI], cr2[NI];
+            bool padrows = false;
 #pragma unroll
+            for (int u = 0; u < NI; ++u) {
+                Lf[u] = (live[u] && f_lft[u]) ? 1.f : 0.f;
+                Rf[u] = (live[u] && f_rgt[u]) ? 1.f : 0.f;
+                cl1[u] = mul2s(c[u][1], Lf[u]); cr2[u] = mul2s(c[u][2], Rf[u]);
+                padrows |= live[u] && (f_top[u] | f_bot[u]);
+            }
+            // products of window row d (g_yuv[k] row q.y - 1 + d, columns q.x - 1 .. q.x + 4) with the tap row in w / acc
+            auto full = [&](int u, const f2* pl, int d, const float (&w)[2][3], f2 (&acc)[2][3]) {
+                f2 row[6];
+                ld6<PN>(pl, (ir[u] + 3 + d) * PN + 2 * (ig[u] + 2), row);
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j & 1][bb] = fma2vv(c[u][j], row[j + 2 - bb], acc[j & 1][bb]);
+                // pad sites' share of Q': rawpad(-1) = raw(1), rawpad(W) = raw(W-2)
+                acc[1][0] = fma2vv(cl1[u], row[1], acc[1][0]);
+                acc[0][2] = fma2vv(cr2[u], row[4], acc[0][2]);
+                if (Cfg::GRAW) {                                        // g_raw(q) += sum_b g_yuv[k](q - (a-1, b-1)) AWq[par(q)][k][a][b]
+                    // site 1 also receives row[1] w[1][0] (L), site 2 row[4] w[0][2] (R); row[i] is column q.x - 1 + i
+                    const float w1_2 = fmaf_(Lf[u], w[1][0], w[1][2]), w2_0 = fmaf_(Rf[u], w[0][2], w[0][0]);
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb) {
+                        graw[u][0] = fma2s(row[2 - bb], w[0][bb], graw[u][0]);
+                        graw[u][3] = fma2s(row[5 - bb], w[1][bb], graw[u][3]);
+                    }
+                    graw[u][1] = fma2s(row[3], w[1][0], fma2s(row[2], w[1][1], fma2s(row[1], w1_2, graw[u][1])));
+                    graw[u][2] = fma2s(row[4], w2_0, fma2s(row[3], w[0][1], fma2s(row[2], w[0][2], graw[u][2])));
+                }
+            };
+#pragma unroll 1
             for (int k = 0; k < 3; ++k) {
-                const f2* pl = k == 0 ? PG : (k == 1 ? PU : PV);
+                const f2* pl = PU + ((k + 2) % 3) * Cfg::kF;            // k = 0: gY0 (PG), 1: gU (PU), 2: gV (PV)
                 const volatile float* awq = &T->AWq[2 * rp][k][0];      // [col phase * 27 + tap], read next to their use
 #pragma unroll
                 for (int A = 0; A < 3; ++A) {
-                    constexpr int NP = 8;                               // 6 Q' sums [col phase][b], then (A == 1 only) 2 P sums
-                    f2 acc[2][3], p2[2];
-                    {
-                        float qa[NP];
-                        if (A == 1) { R2L_PARK_LOAD(6, kB5Q + kB5QStride * k + 6 * A, qa) R2L_PARK_LOAD(2, kB5Q + kB5QStride * k + 18, qa + 6) }
-                        else { R2L_PARK_LOAD(6, kB5Q + kB5QStride * k + 6 * A, qa) qa[6] = qa[7] = 0.f; }
-#pragma unroll
-                        for (int cp = 0; cp < 2; ++cp) {
-#pragma unroll
-                            for (int bb = 0; bb < 3; ++bb) acc[cp][bb] = mk2(qa[cp * 3 + bb], 0.f);
-                            p2[cp] = mk2(qa[6 + cp], 0.f);
-                        }
-                    }
-                    float w[2][3];
+                    f2 acc[2][3];
+                    float qa[8], w[2][3];                               // 6 Q' sums [col phase][b], then (A == 1 only) 2 P sums
+                    if (A == 1) { R2L_PARK_LOAD(6, kB5Q + kB5QStride * k + 6 * A, qa) R2L_PARK_LOAD(2, kB5Q + kB5QStride * k + 18, qa + 6) }
+                    else { R2L_PARK_LOAD(6, kB5Q + kB5QStride * k + 6 * A, qa) }
 #pragma unroll
                     for (int cp = 0; cp < 2; ++cp)
 #pragma unroll
-                        for (int bb = 0; bb < 3; ++bb) w[cp][bb] = awq[cp * 27 + A * 3 + bb];
+                        for (int bb = 0; bb < 3; ++bb) { acc[cp][bb] = mk2(0.f, 0.f); w[cp][bb] = awq[cp * 27 + A * 3 + bb]; }
 #pragma unroll
-                    for (int u = 0; u < NI; ++u) {
-                        if (!live[u]) continue;
-                        auto full = [&](int d, bool centre) {           // window row d = g_yuv[k] row q.y - 1 + d, columns q.x - 1 .. q.x + 4
-                            f2 row[6];
-                            ld6<PN>(pl, (ir[u] + 3 + d) * PN + 2 * (ig[u] + 2), row);
+                    for (int u = 0; u < NI; ++u) full(u, pl, 2 - A, w, acc);
 #pragma unroll
-                            for (int bb = 0; bb < 3; ++bb)
+                    for (int cp = 0; cp < 2; ++cp)
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const f2 t = row[j + 2 - bb];                               // g_yuv[k](q - (a-1, b-1))
-                                    acc[j & 1][bb] = fma2vv(c[u][j], t, acc[j & 1][bb]);
-                                    if (Cfg::GRAW) graw[u][j] = fma2s(t, w[j & 1][bb], graw[u][j]);
-                                }
-                            if (centre) {
+                        for (int bb = 0; bb < 3; ++bb) qa[cp * 3 + bb] += acc[cp][bb].x + acc[cp][bb].y;
+                    R2L_PARK_STORE(6, kB5Q + kB5QStride * k + 6 * A, qa)
+                    if (A == 1) {                                       // P[col phase] = sum of g_yuv[k] over the owned sites
+                        f2 p2[2] = {mk2(0.f, 0.f), mk2(0.f, 0.f)};
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) p2[j & 1] = add2v(p2[j & 1], row[j + 1]);
-                            }
-                            if (f_lft[u]) {                             // pad column -1 -> site 1, tap b = 0
-                                acc[1][0] = fma2vv(c[u][1], row[1], acc[1][0]);
-                                if (Cfg::GRAW) graw[u][1] = fma2s(row[1], w[1][0], graw[u][1]);
-                            }
-                            if (f_rgt[u]) {                             // pad column W -> site 2, tap b = 2
-                                acc[0][2] = fma2vv(c[u][2], row[4], acc[0][2]);
-                                if (Cfg::GRAW) graw[u][2] = fma2s(row[4], w[0][2], graw[u][2]);
-                            }
-                        };
-                        full(2 - A, A == 1);
-                        if (A == 0 && f_top[u]) full(0, false);
-                        if (A == 2 && f_bot[u]) full(2, false);
-                    }
-                    {
-                        float qa[NP];
+                        for (int u = 0; u < NI; ++u) {
+                            f2 row[4];
+                            ld4<PN>(pl, (ir[u] + 4) * PN + 2 * (ig[u] + 2), row);
 #pragma unroll
-                        for (int cp = 0; cp < 2; ++cp) {
-#pragma unroll
-                            for (int bb = 0; bb < 3; ++bb) qa[cp * 3 + bb] = acc[cp][bb].x + acc[cp][bb].y;
-                            qa[6 + cp] = p2[cp].x + p2[cp].y;
+                            for (int j = 0; j < 4; ++j) p2[j & 1] = add2v(p2[j & 1], row[j]);
                         }
+                        qa[6] += p2[0].x + p2[0].y; qa[7] += p2[1].x + p2[1].y;
+                        R2L_PARK_STORE(2, kB5Q + kB5QStride * k + 18, qa + 6)
+                    }
+                }
+            }
+            // reflect-1 pad rows: the row above row 1 acts through tap row 0 on window row 0, the row below row H-2 through
+            // tap row 2 on window row 2.  Only warps that hold image row 1 or H-2 come here.
+            if (R2L_ANY(padrows)) {
+#pragma unroll 1
+                for (int k = 0; k < 3; ++k) {
+                    const f2* pl = PU + ((k + 2) % 3) * Cfg::kF;
+                    const volatile float* awq = &T->AWq[2 * rp][k][0];
+#pragma unroll 1
+                    for (int A = 0; A < 3; A += 2) {
+                        f2 acc[2][3];
+                        float qa[6], w[2][3];
+                        R2L_PARK_LOAD(6, kB5Q + kB5QStride * k + 6 * A, qa)
+#pragma unroll
+                        for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+                            for (int bb = 0; bb < 3; ++bb) { acc[cp][bb] = mk2(0.f, 0.f); w[cp][bb] = awq[cp * 27 + A * 3 + bb]; }
+#pragma unroll
+                        for (int u = 0; u < NI; ++u)
+                            if (live[u] && (A == 0 ? f_top[u] : f_bot[u])) full(u, pl, A, w, acc);
+#pragma unroll
+                        for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+                            for (int bb = 0; bb < 3; ++bb) qa[cp * 3 + bb] += acc[cp][bb].x + acc[cp][bb].y;
                         R2L_PARK_STORE(6, kB5Q + kB5QStride * k + 6 * A, qa)
-                        if (A == 1) { R2L_PARK_STORE(2, kB5Q + kB5QStride * k + 18, qa + 6) }
                     }
                 }
             }
