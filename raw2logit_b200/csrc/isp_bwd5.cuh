@@ -12,7 +12,10 @@
 //   * B7 walks the three gradient planes one after the other (k outermost) with packed (image A, image B)
 //     accumulators: the Q' statistic is one FFMA2 per tap and site pair instead of two scalar FMAs;
 //   * stencil weights are read from shared memory next to their use (uniform-address LDS) instead of sitting in
-//     25 / 54 registers for a whole phase.
+//     25 / 54 registers for a whole phase;
+//   * no software L2 prefetch: prefetch.global.L2 (CCTL.E.PF2) fetches one 32-byte sector per instruction, and both the
+//     fourth generation's one-per-line pattern and a one-per-sector pattern made this kernel SLOWER (99 / 115 us against
+//     94 us without, profiles/r01_v5_summary.md) -- with 16 warps per SM the demand loads are covered well enough.
 // Column layout per thread (also the order of the host emulation's array and of the CTA reduction):
 //   [0,2) gamma sum per stream | [2,27) dWg | [27,36) dWs | [36 + 20 k, +18) Q'[k][tap row][col phase][b] | (+18, +2) P[k][col phase]
 #pragma once
@@ -31,6 +34,15 @@ template <int TH_, int TW_, int NT_, bool GRAW_, bool TAIL_> struct Bwd5Cfg : Bw
 };
 
 inline bool bwd5_shape_ok(int H, int W) { return bwd4_shape_ok(H, W); }
+
+// bit pattern of a float
+R2L_HD unsigned fbits(float x) {
+#ifdef R2L_HOST_EMU
+    unsigned u; std::memcpy(&u, &x, 4); return u;
+#else
+    return __float_as_uint(x);
+#endif
+}
 
 // (x, y) -> one aligned register pair that stays one: a plain make_float2 of values from two different loads is
 // re-packed with two MOVs at every FFMA2 that uses it when registers are tight (profiles/r01_v5_summary.md), and
@@ -105,24 +117,6 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         // clipped values (exact compare without a tail, where o is bit-identical to the forward's; a 1e-4 / 1e-6
         // relative margin behind a tail, where o is recovered by an affine inverse).
         { R2L_FOR_THREADS(NT) {
-#ifndef R2L_HOST_EMU
-            // the centres B5 / B6 / B7 read from global memory (Y1, Y0, raw of the owned rows): pull their lines into L2
-            {
-                constexpr int LPR = TW * 8 / 128;                      // 128-byte lines per owned row of a luma plane
-                for (int i = tid; i < TH * LPR * 2; i += NT) {
-                    const int l = i % LPR, rr = (i / LPR) % TH, pl = i / (LPR * TH);
-                    const int gy = ty0 + rr, gx = tx0 + l * 16;
-                    if (gy < H && gx < W) prefetch_l2((pl ? y1pair : y0pair) + ((size_t)gy * W + gx) * 2);
-                }
-                constexpr int RPL = 128 / (int)sizeof(RawT);           // raw elements per line
-                constexpr int LPRR = (TW + RPL - 1) / RPL;
-                for (int i = tid; i < TH * LPRR * 2; i += NT) {
-                    const int l = i % LPRR, rr = (i / LPRR) % TH, im = i / (LPRR * TH);
-                    const int gy = ty0 + rr, gx = tx0 + l * RPL;
-                    if (gy < H && gx < W) prefetch_l2((im ? imgB : imgA) + (size_t)gy * W + gx);
-                }
-            }
-#endif
             float m2g[9];
             const float invg = T->invg, gam = T->gamma, one_m_g = 1.0f - T->gamma;
 #pragma unroll
@@ -130,28 +124,39 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             const float o_lo_exact = fast_exp2(invg * fast_log2(kClipLo));      // the forward's value of a low clip
             const float o_lo = Cfg::TAIL ? o_lo_exact * (1.0f + 1e-4f) : o_lo_exact;
             const float o_hi = Cfg::TAIL ? 1.0f - 1e-6f : 1.0f;
-            f2 sg = mk2(0.f, 0.f);                                     // sum G o log2(cl), per stream
+            // o_lo < o < o_hi as ONE unsigned compare on the bit patterns (positive floats order like their bits; a
+            // negative or NaN o wraps to a huge difference and fails, as it fails the two float compares)
+            const unsigned m_base = fbits(o_lo) + 1u, m_span = fbits(o_hi) - m_base;
+            // per-tile bases: channel k of image A / B sits k planes further (32-bit offsets inside an image)
+            const float* goA = a.gout + (size_t)b0 * 3 * plane;
+            const float* goB = a.gout + (size_t)b1 * 3 * plane;
+            const float* yoA = a.out + (size_t)b0 * 3 * plane;
+            const float* yoB = a.out + (size_t)b1 * 3 * plane;
+            const int plane_i = (int)plane;
+            f2 sg = mk2(0.f, 0.f);                                     // sum G o log2(o), per stream (x gamma when parked)
+            // owned rectangle first, halo ring after: whole warps are inside or outside the rectangle that carries
+            // the gamma statistic
             for (int item = tid; item < Cfg::FH * GG; item += NT) {
-                const int rr = item / GG, g = item - rr * GG - 1;
-                const int r = rr - 4;
+                int r, g;
+                region_item<TH, G, 4>(item, r, g);
                 const int gy = ty0 + r, gx = tx0 + 4 * g;
                 const bool valid = gy >= 0 && gy < H && gx >= 0 && gx < W;
-                const bool owned = r >= 0 && r < TH && g >= 0 && g < G;
+                const bool owned = item < TH * G;
                 f2 gy2[4], gu[4], gv[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { gy2[j] = mk2(0.f, 0.f); gu[j] = mk2(0.f, 0.f); gv[j] = mk2(0.f, 0.f); }
                 if (valid) {
-                    const size_t pix = (size_t)gy * W + gx;
+                    const int pix = gy * W + gx;
                     f4 ga[3], gb[3], ya[3], yb[3], ad[3];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const size_t oa = ((size_t)b0 * 3 + k) * plane + pix, ob = ((size_t)b1 * 3 + k) * plane + pix;
-                        ga[k] = ld_stream4(a.gout + oa);
-                        ya[k] = ld_stream4(a.out + oa);
-                        gb[k] = ld_stream4(a.gout + ob);
-                        yb[k] = ld_stream4(a.out + ob);
+                        const int off = k * plane_i + pix;
+                        ga[k] = ld_stream4(goA + off);
+                        ya[k] = ld_stream4(yoA + off);
+                        gb[k] = ld_stream4(goB + off);
+                        yb[k] = ld_stream4(yoB + off);
                         ad[k].x = ad[k].y = ad[k].z = ad[k].w = 0.f;
-                        if (Cfg::TAIL && a.additive) ad[k] = *reinterpret_cast<const f4*>(a.additive + (size_t)k * plane + pix);
+                        if (Cfg::TAIL && a.additive) ad[k] = *reinterpret_cast<const f4*>(a.additive + off);
                     }
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
@@ -165,23 +170,27 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            float Ga = gak[j], Gb = dup ? 0.f : gbk[j];
+                            float Ga = gak[j], Gb = gbk[j];             // (an odd batch's duplicate stream is zeroed below)
                             f2 o = mk2(yak[j], ybk[j]);
                             if (Cfg::TAIL) {
                                 Ga = t_gs * (Ga - t_c1 - t_c2 * o.x);
-                                Gb = dup ? 0.f : t_gs * (Gb - t_c1 - t_c2 * o.y);
+                                Gb = t_gs * (Gb - t_c1 - t_c2 * o.y);
                                 o = mk2(fmaf_(o.x, t_isc, t_osh) - adk[j], fmaf_(o.y, t_isc, t_osh) - adk[j]);
                             }
                             const f2 lo = mk2(fast_log2(o.x), fast_log2(o.y));
                             const f2 ex = mul2s(lo, one_m_g);
                             const f2 e = mk2(fast_exp2(ex.x), fast_exp2(ex.y));
-                            if (owned) sg = fma2vv(mk2(Ga * o.x, Gb * o.y), mul2s(lo, gam), sg);
-                            const f2 gr = mk2((o.x > o_lo && o.x < o_hi) ? Ga * e.x : 0.f,
-                                              (o.y > o_lo && o.y < o_hi) ? Gb * e.y : 0.f);
+                            if (owned) sg = fma2vv(mk2(Ga * o.x, Gb * o.y), lo, sg);
+                            const f2 gr = mk2((fbits(o.x) - m_base < m_span) ? Ga * e.x : 0.f,
+                                              (fbits(o.y) - m_base < m_span) ? Gb * e.y : 0.f);
                             gy2[j] = fma2s(gr, m2g[k * 3 + 0], gy2[j]);
                             gu[j] = fma2s(gr, m2g[k * 3 + 1], gu[j]);
                             gv[j] = fma2s(gr, m2g[k * 3 + 2], gv[j]);
                         }
+                    }
+                    if (dup) {                                          // odd batch, last pair: stream B carries no gradient
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { gy2[j].y = 0.f; gu[j].y = 0.f; gv[j].y = 0.f; }
                     }
                 }
                 st4<PN>(PG, (r + 4) * PN + 2 * (g + 2), gy2[0], gy2[1], gy2[2], gy2[3]);
@@ -191,7 +200,8 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             {
                 float v[2];
                 R2L_PARK_LOAD(2, kB5Sg, v)
-                v[0] += sg.x; v[1] += sg.y;
+                v[0] = fmaf_(sg.x, gam, v[0]);
+                if (!dup) v[1] = fmaf_(sg.y, gam, v[1]);
                 R2L_PARK_STORE(2, kB5Sg, v)
             }
         } }
@@ -202,25 +212,6 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         // inside the items of rows 1,2 / H-2,H-3 and of the first / last run of the image.  Y1 centres come from the
         // plane the forward saved.
         { R2L_FOR_THREADS(NT) {
-#ifndef R2L_HOST_EMU
-            // next tile's grad_out / forward-output windows (rows -4..TH+3 of 3 channels x 2 images x 2 tensors) -> L2
-            {
-                const int next = tile + n_cta;
-                if (next < grid.n) {
-                    int nb0, nb1, ny0, nx0;
-                    decode_pair_tile(grid, next, TH, TW, a.B, nb0, nb1, ny0, nx0);
-                    constexpr int LPR = TW * 4 / 128;
-                    const int nl = Cfg::FH * 12 * LPR;
-                    for (int i = tid; i < nl; i += NT) {
-                        const int l = i % LPR, pr = i / LPR, pk = pr % 12, rr = pr / 12;
-                        const int gy = ny0 - 4 + rr, gx = nx0 + l * 32;
-                        const int pk6 = pk % 6, img = pk6 < 3 ? nb0 : nb1, k = pk6 < 3 ? pk6 : pk6 - 3;
-                        if (gy >= 0 && gy < H && gx < W)
-                            prefetch_l2((pk < 6 ? a.gout : a.out) + ((size_t)img * 3 + k) * plane + (size_t)gy * W + gx);
-                    }
-                }
-            }
-#endif
             // The weights are read next to their use (uniform-address LDS; volatile keeps the compiler from hoisting all
             // 25 into registers for the whole phase).
             const volatile float* wg = T->Wg;
