@@ -11,6 +11,9 @@ echo "== bench" ; timeout 600 python bench.py --no-cpu-baseline 2>&1 | tail -1 |
 if [ "${2:-}" == "ab" ]; then
 echo "== bench gen4" ; R2L_ISP_BWD_GEN=4 timeout 600 python bench.py --no-cpu-baseline --steps 100 2>&1 | tail -1 | tee gpurun_out/bench_gen4.json | python -c "$summ"
 fi
+if [ "${3:-}" == "launches" ]; then
+echo "== ncu launch list" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1 ; grep -c isp_ gpurun_out/launches.csv
+fi
 if [ "${1:-}" != "noprof" ]; then
 echo "== ncu full" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:isp_ -s 12 -c 2 -o gpurun_out/prof -f python bench.py --steps 4 --warmup 4 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ; tail -1 gpurun_out/ncu_full.log
 fi

@@ -356,3 +356,43 @@ def test_backward_from_saved_output_agrees_with_full_recompute(shape, tail):
     (pa, ra), (pb, rb) = res
     assert maxabs(pa, pb) <= 2e-5 * max(1.0, pb.abs().max().item()), (shape, tail, maxabs(pa, pb))
     assert maxabs(ra, rb) <= 2e-5 * max(1.0, rb.abs().max().item()), (shape, tail, maxabs(ra, rb))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(5, 256, 256), (2, 96, 200), (3, 72, 136), (1, 8, 8), (2, 37, 8)])
+@pytest.mark.parametrize("tail", ["none", "bn_train", "additive"])
+@pytest.mark.parametrize("u16", [False, True])
+def test_tmem_backward_agrees_with_register_backward(shape, tail, u16):
+    """Fifth-generation backward (running sums parked in tensor memory, the default) against the fourth generation
+    (sums in registers, R2L_ISP_BWD_GEN=4) and the third (no saved luma planes, R2L_ISP_NO_LUMA=1) on multi-tile,
+    partial-tile, odd-batch and tiny shapes, float and uint16 raw, with and without tails; and bit-reproducible."""
+    import os
+    from processing.pipeline_torch import ParametrizedProcessing
+    state = syn.perturbed_state(isp_oracle.default_state(syn.CAMERA_PRESETS["drone"]))
+    raw = syn.smooth_scene(*shape, "drone", seed=43)
+    raw = (syn.to_uint16(raw) if u16 else raw).cuda()
+    g = isp_oracle.cotangent((shape[0], 3, shape[1], shape[2]), "ramp").cuda()
+    res = []
+    for env in ({}, {}, {"R2L_ISP_BWD_GEN": "4"}, {"R2L_ISP_NO_LUMA": "1"}):
+        os.environ.update(env)
+        try:
+            bn = tail.startswith("bn")
+            mod = ParametrizedProcessing(syn.CAMERA_PRESETS["drone"], batch_norm_output=bn)
+            mod.load_state_dict(state, strict=not bn)
+            if tail == "additive":
+                torch.manual_seed(3)
+                mod.additive_layer = torch.nn.Parameter(0.01 * torch.randn(1, 3, shape[1], shape[2]))
+            mod = mod.cuda().train()
+            x = raw.clone() if u16 else raw.clone().requires_grad_(True)
+            mod(x).backward(g)
+            flat = torch.cat([p.grad.flatten() for p in mod.parameters()]).cpu()
+            res.append((flat, None if u16 else x.grad.cpu()))
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    (p5, r5), (p5b, r5b), (p4, r4), (p3, r3) = res
+    assert torch.equal(p5, p5b) and (u16 or torch.equal(r5, r5b)), "TMEM backward is not reproducible run to run"
+    for name, p, r in (("gen4", p4, r4), ("gen3", p3, r3)):
+        assert maxabs(p5, p) <= 2e-5 * max(1.0, p.abs().max().item()), (name, shape, tail, maxabs(p5, p))
+        if not u16:
+            assert maxabs(r5, r) <= 2e-5 * max(1.0, r.abs().max().item()), (name, shape, tail, maxabs(r5, r))
