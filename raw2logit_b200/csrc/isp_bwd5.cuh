@@ -111,6 +111,58 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         const float* y0pair = a.luma + (size_t)(b0 >> 1) * plane * 2;   // Y0 of this image pair, [H][W][2]
         const float* y1pair = y0pair + luma_plane;
 
+        // The centre values a phase reads from global memory (Y1 in B5, Y0 in B6, raw in B7) are requested at the END of
+        // the phase before, ahead of the CTA barrier: the L2 round trip runs while the warp waits for the others
+        // (profiles/r01_v5_summary.md: barrier 1.4 and long-scoreboard 2.1 stall cycles per issued instruction).  The
+        // host emulation, which runs a phase for all threads before the next, loads them at the start of the phase.
+        constexpr int NI5 = TH * G / NT, NI6 = TH * (G / 2) / NT, NI7 = (TH / 2) * G / HALF;
+        static_assert((TH * G) % NT == 0 && (TH * (G / 2)) % NT == 0, "the same number of owned items for every thread");
+        auto load_c5 = [&](int tid, f2 (&c)[NI5][4]) {                  // Y1 centres of B5's owned items
+#pragma unroll
+            for (int u = 0; u < NI5; ++u) {
+                const int item = tid + u * NT;
+                const int r = item / G, g = item - r * G;
+                const int qy = ty0 + r, qx = tx0 + 4 * g;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[u][j] = mk2(0.f, 0.f);
+                if (qy < H && qx < W) ld_luma4(y1pair + ((size_t)qy * W + qx) * 2, c[u]);
+            }
+        };
+        auto load_c6 = [&](int tid, f2 (&c)[NI6][2][4]) {               // Y0 centres of B6's owned (paired) items
+#pragma unroll
+            for (int v = 0; v < NI6; ++v) {
+                const int item = tid + v * NT;
+                const int r = item / (G / 2), g = item - r * (G / 2);
+                const int qy = ty0 + r;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int qx = tx0 + 4 * (g + u * (G / 2));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) c[v][u][j] = mk2(0.f, 0.f);
+                    if (qy < H && qx < W) ld_luma4(y0pair + ((size_t)qy * W + qx) * 2, c[v][u]);
+                }
+            }
+        };
+        auto load_x7 = [&](int tid, f4 (&xa)[NI7], f4 (&xb)[NI7]) {     // fp32 raw centres of B7's items (packed there)
+            const int rp = (tid >> 5) & 1, slot = ((tid >> 6) << 5) | (tid & 31);
+#pragma unroll
+            for (int u = 0; u < NI7; ++u) {
+                const int i = slot + u * HALF;
+                const int ri = i / G, g = i - ri * G;
+                const int qy = ty0 + rp + 2 * ri, qx = tx0 + 4 * g;
+                xa[u].x = xa[u].y = xa[u].z = xa[u].w = 0.f;
+                xb[u] = xa[u];
+                if (sizeof(RawT) == 4 && qy < H && qx < W) {
+                    xa[u] = ld_stream4(reinterpret_cast<const float*>(imgA) + (size_t)qy * W + qx);
+                    xb[u] = ld_stream4(reinterpret_cast<const float*>(imgB) + (size_t)qy * W + qx);
+                }
+            }
+        };
+#ifndef R2L_HOST_EMU
+        f2 c5[NI5][4], c6[NI6][2][4];
+        f4 xa7[NI7], xb7[NI7];
+#endif
+
         // ---- B4: grad_out pulled back through gamma / clip / YUV->RGB to (gY2, gU, gV) on rows -4..TH+3, runs -1..G;
         // gamma statistic.  o = y (or (y - shift)/scale - additive behind a tail); with lo = log2(o):
         // e = cl^(1/g - 1) = 2^((1 - g) lo), log2(cl) = g lo, and the clamp passed iff o lies strictly between its two
@@ -204,6 +256,9 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 if (!dup) v[1] = fmaf_(sg.y, gam, v[1]);
                 R2L_PARK_STORE(2, kB5Sg, v)
             }
+#ifndef R2L_HOST_EMU
+            load_c5(tid, c5);
+#endif
         } }
         R2L_SYNC();
 
@@ -219,9 +274,12 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             // thread's items, so only that row's five packed (image A, image B) sums are live (parked per tap row).
             // Tap row A reaches window row 4 - A; the folded pad contributions that use tap row A ride in the same pass.
             {
-                constexpr int NI5 = TH * G / NT;
-                static_assert((TH * G) % NT == 0, "B5: the same number of owned items for every thread");
-                f2 c[NI5][4], out[NI5][4];
+#ifdef R2L_HOST_EMU
+                f2 c5[NI5][4];
+                load_c5(tid, c5);
+#endif
+                f2 (&c)[NI5][4] = c5;
+                f2 out[NI5][4];
                 int ir[NI5], ig[NI5], rt[NI5];
                 bool inside[NI5], lft[NI5], rgt[NI5];
 #pragma unroll
@@ -235,8 +293,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     // row type of the folded-onto rows: 1 -> row 1, 2 -> row 2, 3 -> row H-2, 4 -> row H-3
                     rt[u] = qy == 1 ? 1 : (qy == 2 ? 2 : (qy == H - 2 ? 3 : (qy == H - 3 ? 4 : 0)));
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { out[u][j] = mk2(0.f, 0.f); c[u][j] = mk2(0.f, 0.f); }
-                    if (inside[u]) ld_luma4(y1pair + ((size_t)qy * W + qx) * 2, c[u]);
+                    for (int j = 0; j < 4; ++j) out[u][j] = mk2(0.f, 0.f);
                 }
                 // Pad columns (reflect-2 of the sharpened plane: -1 -> site 1, -2 -> site 2, W -> site W-2, W+1 -> W-3) are
                 // realised on the data, so the loop is straight-line code: the adjoint of the first / last run of the image
@@ -362,6 +419,9 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 }
                 st4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), out[0], out[1], out[2], out[3]);
             }
+#ifndef R2L_HOST_EMU
+            load_c6(tid, c6);
+#endif
         } }
         R2L_SYNC();
 
@@ -377,16 +437,18 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
                 for (int t = 0; t < 9; ++t) ws2[t] = mk2(wa[t], 0.f);
             }
-            auto b6 = [&](auto NRc, int r, int g, bool owned) {
+#ifdef R2L_HOST_EMU
+            f2 c6[NI6][2][4];
+            load_c6(tid, c6);
+#endif
+            auto b6 = [&](auto NRc, int r, int g, bool owned, const f2 (*pre)[4]) {
                 constexpr int NR = decltype(NRc)::value;
                 const int qy = ty0 + r;
                 f2 c[NR][4], out[NR][4];
 #pragma unroll
                 for (int u = 0; u < NR; ++u) {
-                    const int qx = tx0 + 4 * (g + u * (G / 2));
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { out[u][j] = mk2(0.f, 0.f); c[u][j] = mk2(0.f, 0.f); }
-                    if (owned && qy < H && qx < W) ld_luma4(y0pair + ((size_t)qy * W + qx) * 2, c[u]);
+                    for (int j = 0; j < 4; ++j) { out[u][j] = mk2(0.f, 0.f); c[u][j] = owned ? pre[u][j] : mk2(0.f, 0.f); }
                 }
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
@@ -420,12 +482,15 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     st4<PN>(PG, (r + 4) * PN + 2 * (g + u * (G / 2) + 2), out[u][0], out[u][1], out[u][2], out[u][3]);
                 }
             };
-            for (int item = tid; item < TH * (G / 2); item += NT)       // owned rectangle: paired items
-                b6(std::integral_constant<int, 2>(), item / (G / 2), item % (G / 2), true);
+#pragma unroll
+            for (int v = 0; v < NI6; ++v) {                             // owned rectangle: paired items
+                const int item = tid + v * NT;
+                b6(std::integral_constant<int, 2>(), item / (G / 2), item % (G / 2), true, c6[v]);
+            }
             for (int item = TH * G + tid; item < (TH + 2) * GG; item += NT) {      // halo ring, single runs
                 int r, g;
                 region_item<TH, G, 1>(item, r, g);
-                b6(std::integral_constant<int, 1>(), r, g, false);
+                b6(std::integral_constant<int, 1>(), r, g, false, nullptr);
             }
             {
                 float wa[9];
@@ -433,6 +498,9 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 for (int t = 0; t < 9; ++t) wa[t] = ws2[t].x + ws2[t].y;
                 R2L_PARK_STORE(9, kB5Ws, wa)
             }
+#ifndef R2L_HOST_EMU
+            load_x7(tid, xa7, xb7);
+#endif
         } }
         R2L_SYNC();
 
@@ -444,8 +512,12 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         // (2) on window row 0 (2), pad columns through taps b = 0 / 2 of the first / last run.
         { R2L_FOR_THREADS(NT) {
             const int rp = (tid >> 5) & 1, slot = ((tid >> 6) << 5) | (tid & 31);
-            constexpr int NI = (TH / 2) * G / HALF;
+            constexpr int NI = NI7;
             const float one = a.B > 0 ? 1.f : 2.f;                     // 1.0 the compiler cannot see (pack2)
+#ifdef R2L_HOST_EMU
+            f4 xa7[NI7], xb7[NI7];
+            load_x7(tid, xa7, xb7);
+#endif
             f2 c[NI][4], graw[NI][4];
             int ir[NI], ig[NI];
             bool live[NI], f_top[NI], f_bot[NI], f_lft[NI], f_rgt[NI];
@@ -462,8 +534,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 for (int j = 0; j < 4; ++j) { c[u][j] = mk2(0.f, 0.f); graw[u][j] = mk2(0.f, 0.f); }
                 if (live[u]) {                                          // raw centres of the 4 sites, packed once
                     if (sizeof(RawT) == 4) {
-                        const f4 xa = ld_stream4(reinterpret_cast<const float*>(imgA) + (size_t)qy * W + qx);
-                        const f4 xb = ld_stream4(reinterpret_cast<const float*>(imgB) + (size_t)qy * W + qx);
+                        const f4 xa = xa7[u], xb = xb7[u];
                         c[u][0] = pack2(xa.x, xb.x, one); c[u][1] = pack2(xa.y, xb.y, one); c[u][2] = pack2(xa.z, xb.z, one); c[u][3] = pack2(xa.w, xb.w, one);
                     } else {
 #pragma unroll
