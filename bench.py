@@ -204,7 +204,25 @@ def run_ours(args):
                                  vp(outs[s].data_ptr()), vp(lumas[s].data_ptr()), sp)
         return rc, s
 
+    # N > 1: the 132-float gradient all-reduce is fused into the backward kernel (its last CTA exchanges the gradients over
+    # NVLink peer memory, r2l_isp_backward_dp); NCCL is the fallback when symmetric memory cannot be set up
+    xch = None
+    if world > 1 and os.environ.get("R2L_BENCH_NCCL", "0") != "1":
+        try:
+            from raw2logit_b200 import parallel
+            xch = parallel.PeerExchange()
+        except Exception as e:                                      # noqa: BLE001 - report and fall back
+            if rank == 0:
+                print(f"[bench] fused exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            xch = None
+
     def step_backward(s):
+        if xch is not None:
+            d = xch.next(average=False)
+            return lib.r2l_isp_backward_dp(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, H, W, ctypes.byref(params),
+                                           vp(gouts[s].data_ptr()), None, None, vp(outs[s].data_ptr()),
+                                           vp(lumas[s].data_ptr()), vp(graws[s].data_ptr()),
+                                           vp(gpar.data_ptr()), vp(wsb.data_ptr()), nws, ctypes.byref(d), sp)
         return lib.r2l_isp_backward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, H, W, ctypes.byref(params),
                                     vp(gouts[s].data_ptr()), None, None, vp(outs[s].data_ptr()),
                                     vp(lumas[s].data_ptr()), vp(graws[s].data_ptr()),
@@ -220,7 +238,7 @@ def run_ours(args):
         rc, s = step_kernels(i)
         _lib.check(rc, "forward")
         _lib.check(step_backward(s), "backward")
-        if world > 1:
+        if world > 1 and xch is None:
             dist.all_reduce(gpar)
     K = args.steps
     sampler = ClockSampler(local)
@@ -232,7 +250,7 @@ def run_ours(args):
     for i in range(K):
         rc, s = step_kernels(i)
         rc2 = step_backward(s)
-        if world > 1:
+        if world > 1 and xch is None and os.environ.get("R2L_BENCH_NO_EXCHANGE", "0") != "1":
             dist.all_reduce(gpar)
     t_end.record()
     barrier()
@@ -337,7 +355,11 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(args), gradient_exchange=(
+            "none (1 GPU)" if world == 1 else
+            "fused into the backward kernel: one-shot all-reduce of the 132 gradients over NVLink peer memory "
+            "(r2l_isp_backward_dp)" if xch is not None else "NCCL all-reduce of the 132 gradients after the backward")),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pix * 4, "d2h_bytes_per_step": 132 * 4,
                 "steps": e2e_steps, "api": "ParametrizedProcessing.forward + autograd backward; fp32 raw batch copied "
                                            "from pinned host memory every step on a prefetch stream (double-buffered)"},

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define R2L_ABI_VERSION 3
+#define R2L_ABI_VERSION 4
 
 enum {
     R2L_OK = 0,
@@ -139,6 +139,33 @@ int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int 
                      const r2l_isp_params* params, const float* grad_out, const float* grad_tail,
                      const float* additive, const float* out, const float* saved_luma, float* grad_raw,
                      float* grad_params, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Data-parallel variant (new build: the reference is single-GPU, train.py:362): the same backward, and the
+ * 132 parameter gradients leave the call ALREADY SUMMED OVER ALL RANKS.  The last CTA of the launch -- the one that
+ * turns the per-CTA sums into the gradients -- writes them, each as an 8-byte {value, epoch} word, into its slot of every
+ * rank's exchange buffer over NVLink peer memory, polls the other ranks' slots in its own buffer until they carry the
+ * epoch and adds them up in rank order (bit-identical result on every rank): a one-shot all-reduce of 528 bytes inside
+ * the kernel, no fence, no flag, no collective launch.  grad_raw stays local (images are independent).
+ *   peers     DEVICE array of `world` pointers; peers[r] = rank r's exchange buffer as mapped into THIS process
+ *             (CUDA IPC / symmetric memory, e.g. torch.distributed._symmetric_memory: buffer_ptrs_dev), each
+ *             r2l_isp_exchange_bytes(world) bytes, zero-filled once before the first call
+ *   epoch     1, 2, 3, ... -- the same value on every rank, incremented on every call that uses the buffer
+ *   scale     factor applied to the sum (1/world for an average, 1 for a sum)
+ * Needs the path that finishes the gradients in the launch (out and saved_luma given, shape served by the vectorised
+ * kernel); otherwise R2L_ERR_BAD_ARGUMENT and nothing is launched (use r2l_isp_backward + a collective).  Every rank
+ * must make the call, or the others wait for ever, as with any collective. */
+typedef struct {
+    int world, rank;
+    float* const* peers;
+    unsigned epoch;
+    float scale;
+} r2l_isp_allreduce;
+size_t r2l_isp_exchange_bytes(int world);
+int r2l_isp_backward_dp(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
+                        const r2l_isp_params* params, const float* grad_out, const float* grad_tail,
+                        const float* additive, const float* out, const float* saved_luma, float* grad_raw,
+                        float* grad_params, void* workspace, size_t workspace_bytes, const r2l_isp_allreduce* dp,
+                        void* stream);
 
 /* out[c][i] = scale[c] * sum_b x[b][c][i]  (scale may be NULL): gradient of the broadcast additive_layer
  * (pipeline_torch.py:212-214), x = grad_out (B,C,HW), out (C,HW).  Deterministic (fixed summation order). */

@@ -18,12 +18,18 @@ GRAD_LAYOUT = {
     "gauss_weight": (107, 25, (1, 1, 5, 5)),
 }
 F32, U16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = ("r2l_isp_abi_version", "r2l_isp_error_string", "r2l_isp_last_cuda_error", "r2l_isp_forward",
            "r2l_isp_workspace_bytes", "r2l_isp_forward_bn_train", "r2l_isp_bn_backward_prepare", "r2l_isp_backward",
            "r2l_isp_mosaic", "r2l_isp_mosaic_backward", "r2l_isp_batch_sum", "r2l_isp_saved_luma_floats",
-           "r2l_isp_luma_supported")
+           "r2l_isp_luma_supported", "r2l_isp_exchange_bytes", "r2l_isp_backward_dp")
+
+
+class IspAllreduce(ctypes.Structure):
+    """r2l_isp_allreduce (include/r2l_isp.h): the data-parallel exchange fused into the backward kernel."""
+    _fields_ = [("world", ctypes.c_int), ("rank", ctypes.c_int), ("peers", ctypes.c_void_p), ("epoch", ctypes.c_uint),
+                ("scale", ctypes.c_float)]
 
 
 class IspParams(ctypes.Structure):
@@ -69,6 +75,11 @@ def load():
     lib.r2l_isp_backward.restype = ci
     lib.r2l_isp_backward.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(IspParams), vp, vp, vp, vp, vp, vp, vp, vp, sz,
                                      vp]
+    lib.r2l_isp_backward_dp.restype = ci
+    lib.r2l_isp_backward_dp.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(IspParams), vp, vp, vp, vp, vp, vp, vp, vp,
+                                        sz, ctypes.POINTER(IspAllreduce), vp]
+    lib.r2l_isp_exchange_bytes.restype = sz
+    lib.r2l_isp_exchange_bytes.argtypes = [ci]
     lib.r2l_isp_mosaic.restype = ci
     lib.r2l_isp_mosaic.argtypes = [vp, ci, cf, ci, ci, ci, vp, ci, ci, vp, vp]
     lib.r2l_isp_mosaic_backward.restype = ci

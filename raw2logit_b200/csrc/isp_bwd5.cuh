@@ -61,6 +61,43 @@ struct Bwd5Acc { float sums[kBwd5AccFloats]; };
 #define R2L_PARK_STORE(N, col, v) { __syncwarp(); tmem::store<N>(tacc + (col), v); tmem::wait_st(); }
 #endif
 
+#ifndef R2L_HOST_EMU
+// ---- one-shot all-reduce of the 132 gradients over NVLink peer memory, run by the CTA that finished them ------------
+// (r2l_isp_backward_dp, include/r2l_isp.h).  Every gradient travels as one 8-byte word {value, epoch}: an aligned
+// 64-bit store is single-copy atomic, so the epoch tag tells the reader that the value next to it is this step's -- no
+// fence, no separate flag, one NVLink one-way latency.  Push: thread e writes word e of this rank's slot on EVERY rank.
+// Pull: thread e polls word e of every rank's slot in OUR buffer until it carries the epoch and adds the values in
+// rank order -- the same order everywhere, so all ranks hold bit-identical sums.  Slots are double-buffered by epoch
+// parity: a rank that already pushes step i + 1 cannot overwrite what a slower rank still reads for step i, and it
+// cannot reach step i + 2 before that rank has pushed step i + 1.
+__device__ __forceinline__ void st_tagged_sys(float* p, float v, unsigned tag) {
+    asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ float ld_tagged_sys(const float* p, unsigned tag) {
+    unsigned v, t;
+    do {
+        asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(p) : "memory");
+    } while (t != tag);
+    return __uint_as_float(v);
+}
+template <int NT> __device__ __forceinline__ void peer_allreduce(const BwdArgs& a) {
+    static_assert(kSlotPitch >= R2L_NUM_PARAM_GRADS, "one tagged word per gradient");
+    const int world = a.world, tid = threadIdx.x;
+    const size_t slot0 = (size_t)(a.epoch & 1u) * world * (2 * kSlotPitch);      // floats; a slot = kSlotPitch words of 8 bytes
+    __syncthreads();                                                     // a.grads of this launch are written
+    for (int i = tid; i < world * R2L_NUM_PARAM_GRADS; i += NT) {
+        const int p = i / R2L_NUM_PARAM_GRADS, e = i - p * R2L_NUM_PARAM_GRADS;
+        st_tagged_sys(a.peers[p] + slot0 + (size_t)a.rank * (2 * kSlotPitch) + 2 * e, a.grads[e], a.epoch);
+    }
+    const float* mine = a.peers[a.rank] + slot0;
+    for (int e = tid; e < R2L_NUM_PARAM_GRADS; e += NT) {
+        float sum = 0.f;
+        for (int r = 0; r < world; ++r) sum += ld_tagged_sys(mine + (size_t)r * (2 * kSlotPitch) + 2 * e, a.epoch);
+        a.grads[e] = sum * a.dp_scale;
+    }
+}
+#endif
+
 template <class Cfg, typename RawT>
 R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid, float* smem) {
     constexpr int TH = Cfg::TH, TW = Cfg::TW, NT = Cfg::NT, PN = Cfg::PN, G = Cfg::G, HALF = Cfg::HALF;
@@ -727,6 +764,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             __threadfence();
             static_assert((size_t)(NT / 32 + 1) * kStatPitch * 8 + 130 * 8 <= (size_t)Cfg::kSites * 8, "finish scratch fits the planes");
             fused_finish<NT>(T, a.partials, n_cta, a.grads, reinterpret_cast<double*>(PU));
+            if (a.world > 1) peer_allreduce<NT>(a);
         }
     }
 #endif

@@ -431,6 +431,8 @@ struct BwdAcc {
 };
 constexpr int kStatGamma = 0, kStatWg = 1, kStatWs = 26, kStatQ = 35, kStatP = 143, kNumStats = 155;
 constexpr int kStatPitch = 160;
+// exchange buffer of the fused all-reduce: [2 epoch parities][world][kSlotPitch] 8-byte words {value, epoch tag}
+constexpr int kSlotPitch = 136, kMaxWorld = 16;
 R2L_HD int stat_q_index(int k, int par, int t) { return kStatQ + (k * 4 + par) * 9 + t; }
 R2L_HD int stat_p_index(int k, int par) { return kStatP + k * 4 + par; }
 
@@ -470,6 +472,11 @@ struct BwdArgs {
     unsigned* ticket = nullptr;    // device counter (zero on entry) for the fused finish: the last CTA to publish its
                                    // partial sums turns them into the 132 gradients (null: separate finish kernel)
     float* grads = nullptr;        // destination of the fused finish
+    // data-parallel exchange fused into the finish (r2l_isp_backward_dp): peers[r] = rank r's exchange buffer
+    float* const* peers = nullptr;
+    int world = 1, rank = 0;
+    unsigned epoch = 0;
+    float dp_scale = 1.f;
 };
 
 // gather of the transposed 5x5 at a (possibly padded) site q': sum_ij Wg[ij] * gY2(q' - (i-2, j-2)), in-image only

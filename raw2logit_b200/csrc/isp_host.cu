@@ -411,6 +411,10 @@ static int launch_backward_any(const BwdArgs& a, int raw_dtype, float* grads, cu
     int g = 0;
     int rc = kNotServed;
     const char* force = getenv("R2L_ISP_FORCE_GENERIC");        // debugging knob
+    if (a.world > 1) {                                          // the fused exchange lives in the fifth generation only
+        const char* gen = getenv("R2L_ISP_BWD_GEN");
+        if ((force && force[0] == '1') || (gen && gen[0] == '4') || !(a.out && a.luma)) return R2L_ERR_BAD_ARGUMENT;
+    }
     if (!(force && force[0] == '1')) {
         if (a.out && a.luma) {                                  // fourth / fifth generation: nothing recomputed, fused finish
             BwdArgs a4 = a;
@@ -423,6 +427,7 @@ static int launch_backward_any(const BwdArgs& a, int raw_dtype, float* grads, cu
                 rc = raw_dtype == R2L_F32 ? launch_backward5_f32(a4, st, &g) : launch_backward5_u16(a4, st, &g);
             if (rc == R2L_OK) return rc;
         }
+        if (a.world > 1) return rc == kNotServed ? (int)R2L_ERR_BAD_ARGUMENT : rc;   // the exchange lives in that kernel only
         if (rc == kNotServed) rc = raw_dtype == R2L_F32 ? launch_backward3_f32(a, st, &g) : launch_backward3_u16(a, st, &g);
     }
     if (rc == kNotServed) rc = launch_backward_generic(a, raw_dtype, st, &g);
@@ -536,10 +541,44 @@ int r2l_isp_bn_backward_prepare(const float* grad_out, const float* out, const f
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);
 }
 
+size_t r2l_isp_exchange_bytes(int world) {
+    if (world < 1 || world > kMaxWorld) return 0;
+    return (size_t)2 * world * kSlotPitch * 8;
+}
+
+static int backward_impl(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
+                         const r2l_isp_params* params, const float* grad_out, const float* grad_tail,
+                         const float* additive, const float* out, const float* saved_luma, float* grad_raw,
+                         float* grad_params, void* workspace, size_t workspace_bytes, const r2l_isp_allreduce* dp,
+                         void* stream);
+
 int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
                      const r2l_isp_params* params, const float* grad_out, const float* grad_tail,
                      const float* additive, const float* out, const float* saved_luma, float* grad_raw,
                      float* grad_params, void* workspace, size_t workspace_bytes, void* stream) {
+    return backward_impl(raw, raw_dtype, raw_denominator, B, H, W, params, grad_out, grad_tail, additive, out, saved_luma,
+                         grad_raw, grad_params, workspace, workspace_bytes, nullptr, stream);
+}
+
+int r2l_isp_backward_dp(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
+                        const r2l_isp_params* params, const float* grad_out, const float* grad_tail,
+                        const float* additive, const float* out, const float* saved_luma, float* grad_raw,
+                        float* grad_params, void* workspace, size_t workspace_bytes, const r2l_isp_allreduce* dp,
+                        void* stream) {
+    if (!dp) return R2L_ERR_NULL_POINTER;
+    if (dp->world < 1 || dp->world > kMaxWorld || dp->rank < 0 || dp->rank >= dp->world || dp->epoch == 0)
+        return R2L_ERR_BAD_ARGUMENT;
+    if (dp->world > 1 && !dp->peers) return R2L_ERR_NULL_POINTER;
+    if (B <= 0) return R2L_ERR_BAD_ARGUMENT;                  // an empty shard cannot take part in the exchange
+    return backward_impl(raw, raw_dtype, raw_denominator, B, H, W, params, grad_out, grad_tail, additive, out, saved_luma,
+                         grad_raw, grad_params, workspace, workspace_bytes, dp, stream);
+}
+
+static int backward_impl(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
+                         const r2l_isp_params* params, const float* grad_out, const float* grad_tail,
+                         const float* additive, const float* out, const float* saved_luma, float* grad_raw,
+                         float* grad_params, void* workspace, size_t workspace_bytes, const r2l_isp_allreduce* dp,
+                         void* stream) {
     int rc = check_common(raw, raw_dtype, B, H, W, params);
     if (rc != R2L_OK) return rc;
     if (!grad_params || !workspace || (B > 0 && !grad_out)) return R2L_ERR_NULL_POINTER;
@@ -557,6 +596,9 @@ int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int 
     a.out = out;
     a.luma = out ? saved_luma : nullptr;
     if (out && additive && !grad_tail) return R2L_ERR_BAD_ARGUMENT;   // an additive tail needs grad_tail to invert it
+    if (dp && dp->world > 1) {
+        a.peers = dp->peers; a.world = dp->world; a.rank = dp->rank; a.epoch = dp->epoch; a.dp_scale = dp->scale;
+    }
     return launch_backward_any(a, raw_dtype, grad_params, st);
 }
 

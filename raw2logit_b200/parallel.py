@@ -60,3 +60,39 @@ def data_parallel_step(model, batch, optimizer=None, rank=0, world=1, group=None
     if optimizer is not None:
         optimizer.step()
     return loss.detach()
+
+
+class PeerExchange:
+    """Exchange buffers of the all-reduce that is fused into the backward kernel (``r2l_isp_backward_dp``,
+    include/r2l_isp.h): one symmetric-memory allocation per rank, every rank's buffer mapped into every process, so
+    the kernel's last CTA pushes its 132 gradients to all ranks over NVLink and adds the slots up itself -- no
+    collective launch.  ``next()`` hands out the per-call descriptor (the epoch must advance in lock step on all
+    ranks, i.e. every rank makes every call).
+
+    Needs one process per GPU on one node with peer access (``torch.distributed._symmetric_memory``).  The gradients
+    of the task model still go through ``allreduce_gradients`` (NCCL); this object serves the ISP-only step."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised process group")
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        nbytes = _lib.load().r2l_isp_exchange_bytes(self.world)
+        if nbytes == 0:
+            raise RuntimeError(f"world size {self.world} is not served by the fused exchange")
+        self.buffer = symm.empty(nbytes // 4, dtype=torch.float32, device=device)
+        self.buffer.zero_()
+        self.handle = symm.rendezvous(self.buffer, group.group_name)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                          # every rank's flags are zero before anyone writes
+        self.peers = int(self.handle.buffer_ptrs_dev)                # device array of `world` buffer pointers
+        self.epoch = 0
+
+    def next(self, average=True):
+        """Descriptor for the next ``r2l_isp_backward_dp`` call (``_lib.IspAllreduce``)."""
+        from . import _lib
+        self.epoch += 1
+        return _lib.IspAllreduce(self.world, self.rank, self.peers, self.epoch, 1.0 / self.world if average else 1.0)
