@@ -215,6 +215,11 @@ def run_ours(args):
             if rank == 0:
                 print(f"[bench] fused exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
             xch = None
+        # all ranks must take the same path (a rank that waits in the fused exchange for one that went to NCCL never returns)
+        ok = torch.tensor([1 if xch is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            xch = None
 
     def step_backward(s):
         if xch is not None:
