@@ -41,9 +41,9 @@ def main():
         nws = lib.r2l_isp_workspace_bytes(B, size, size)
         ws = torch.empty(nws // 4, device=dev)
 
-        def fwd(s):
+        def fwd(s, save_luma=True):            # the static (frozen) processor has no backward: no luma planes to keep
             return lib.r2l_isp_forward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, size, size, ctypes.byref(params),
-                                       None, vp(outs[s].data_ptr()), vp(lumas[s].data_ptr()), sp)
+                                       None, vp(outs[s].data_ptr()), vp(lumas[s].data_ptr()) if save_luma else None, sp)
 
         def bwd(s, need_raw):
             return lib.r2l_isp_backward(vp(raws[s].data_ptr()), _lib.F32, 65535.0, B, size, size, ctypes.byref(params),
@@ -63,10 +63,11 @@ def main():
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / n
 
+        t_fs = time_it(lambda s: fwd(s, False))
         t_f = time_it(fwd)
         t_b = time_it(lambda s: bwd(s, True))
         t_bn = time_it(lambda s: bwd(s, False))
-        for mode, ms, bpp in (("static: forward only", t_f, 16), ("parametrized: forward + backward (raw grad)", t_f + t_b, 36),
+        for mode, ms, bpp in (("static: forward only", t_fs, 16), ("parametrized: forward + backward (raw grad)", t_f + t_b, 36),
                               ("parametrized: forward + backward (no raw grad)", t_f + t_bn, 32)):
             gbs = bpp * pix / (ms * 1e-3) / 1e9
             print(json.dumps({"size": size, "batch": B, "mode": mode, "ms": round(ms, 4),
