@@ -1,14 +1,11 @@
 // isp_bwd5_tu.cuh -- fifth-generation backward kernels + launcher for one raw element type
 #pragma once
 #include "isp_launch.h"
-#ifndef R2L_B5_MINB
-#define R2L_B5_MINB CPS
-#endif
 
 namespace r2l {
 
 template <class Cfg, typename RawT, int CPS>
-__global__ void __launch_bounds__(Cfg::NT, R2L_B5_MINB) isp_backward5_kernel(BwdArgs a, TileGrid grid) {
+__global__ void __launch_bounds__(Cfg::NT, CPS) isp_backward5_kernel(BwdArgs a, TileGrid grid) {
     extern __shared__ __align__(128) float smem[];
     bwd5_cta<Cfg, RawT>(blockIdx.x, gridDim.x, a, grid, smem);
 }

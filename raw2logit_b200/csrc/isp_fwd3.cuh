@@ -215,36 +215,73 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
         } }
         R2L_SYNC();
 
-        // ---- F3: Y1 = sharpen(Y0) on rows -2..TH+1, runs -1..G (1x4 runs); overwrites the raw window -----------------
+        // ---- F3: Y1 = sharpen(Y0) on rows -2..TH+1, runs -1..G; overwrites the raw window --------------------------------
+        // Items are 3x4 register micro-tiles (three Y1 rows of one run from five Y0 rows: 20 window loads for 108 FFMA2
+        // instead of 36).  A pad row of Y1 (Gaussian reflect-2 of the sharpened plane) is the stencil at the MIRRORED row;
+        // a micro-tile that holds one (first / last block of a border tile) takes its rows one by one.
         { R2L_FOR_THREADS(NT) {
+            static_assert(Cfg::Y1H % 3 == 0, "F3 micro-tiles of three rows");
             float ws[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) ws[t] = T->Ws[t];
-            for (int item = tid; item < Cfg::Y1H * GG; item += NT) {
-                const int rr = item / GG, g = item - rr * GG - 1;
-                const int gy = ty0 - 2 + rr, gx = tx0 + 4 * g;
+            for (int item = tid; item < (Cfg::Y1H / 3) * GG; item += NT) {
+                const int blk = item / GG, g = item - blk * GG - 1;
+                const int rr0 = 3 * blk;
+                const int gx = tx0 + 4 * g;
                 if (gx < 0 || gx >= W) continue;
-                int sr = rr;                                           // Y0 rows sr .. sr+2 <-> image rows gy-1 .. gy+1
-                if ((gy < 0 && gy >= -2) || (gy >= H && gy <= H + 1)) sr = mirror(gy, H) - (ty0 - 2);
                 const int q = 2 + g;
-                f2 acc[4] = {mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f), mk2(0.f, 0.f)};
+                const int gy0 = ty0 - 2 + rr0;
+                f2 acc[3][4];
 #pragma unroll
-                for (int aa = 0; aa < 3; ++aa) {
-                    f2 in[6];
-                    ld6<P>(Y0, (sr + aa) * P + 2 * q, in);
+                for (int o = 0; o < 3; ++o)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < 4; ++j) acc[o][j] = mk2(0.f, 0.f);
+                const bool plain = gy0 >= 0 && gy0 + 2 < H;            // no pad row among the three
+                if (plain) {
 #pragma unroll
-                        for (int bb = 0; bb < 3; ++bb) acc[j] = fma2s(in[j + bb], ws[aa * 3 + bb], acc[j]);
+                    for (int ir = 0; ir < 5; ++ir) {                   // Y0 rows rr0 .. rr0+4 <-> image rows gy0-1 .. gy0+3
+                        f2 in[6];
+                        ld6<P>(Y0, (rr0 + ir) * P + 2 * q, in);
+#pragma unroll
+                        for (int o = 0; o < 3; ++o) {
+                            const int aa = ir - o;
+                            if (aa >= 0 && aa < 3) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                    for (int bb = 0; bb < 3; ++bb) acc[o][j] = fma2s(in[j + bb], ws[aa * 3 + bb], acc[o][j]);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int o = 0; o < 3; ++o) {
+                        const int rr = rr0 + o, gy = gy0 + o;
+                        int sr = rr;                                   // Y0 rows sr .. sr+2 <-> image rows gy-1 .. gy+1
+                        if ((gy < 0 && gy >= -2) || (gy >= H && gy <= H + 1)) sr = mirror(gy, H) - (ty0 - 2);
+#pragma unroll
+                        for (int aa = 0; aa < 3; ++aa) {
+                            f2 in[6];
+                            ld6<P>(Y0, (sr + aa) * P + 2 * q, in);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int bb = 0; bb < 3; ++bb) acc[o][j] = fma2s(in[j + bb], ws[aa * 3 + bb], acc[o][j]);
+                        }
+                    }
                 }
-                if (a.luma && rr >= 2 && rr < TH + 2 && g >= 0 && g < G && gy < H) {     // owned, in the image: keep Y1
-                    float* dst = a.luma + ((((size_t)((a.B + 1) >> 1) + (b0 >> 1)) * H + gy) * W + gx) * 2;
-                    st2(reinterpret_cast<f2*>(dst), acc[0], acc[1]);
-                    st2(reinterpret_cast<f2*>(dst) + 2, acc[2], acc[3]);
+#pragma unroll
+                for (int o = 0; o < 3; ++o) {
+                    const int rr = rr0 + o, gy = gy0 + o;
+                    if (a.luma && rr >= 2 && rr < TH + 2 && g >= 0 && g < G && gy < H) {     // owned, in the image: keep Y1
+                        float* dst = a.luma + ((((size_t)((a.B + 1) >> 1) + (b0 >> 1)) * H + gy) * W + gx) * 2;
+                        st2(reinterpret_cast<f2*>(dst), acc[o][0], acc[o][1]);
+                        st2(reinterpret_cast<f2*>(dst) + 2, acc[o][2], acc[o][3]);
+                    }
+                    st4<P>(Y1, rr * P + 2 * q, acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
+                    if (gx == 0) { Y1[rr * P + phys<P>(4 * q - 1)] = acc[o][1]; Y1[rr * P + phys<P>(4 * q - 2)] = acc[o][2]; }
+                    if (gx + 4 == W) { Y1[rr * P + phys<P>(4 * q + 4)] = acc[o][2]; Y1[rr * P + phys<P>(4 * q + 5)] = acc[o][1]; }
                 }
-                st4<P>(Y1, rr * P + 2 * q, acc[0], acc[1], acc[2], acc[3]);
-                if (gx == 0) { Y1[rr * P + phys<P>(4 * q - 1)] = acc[1]; Y1[rr * P + phys<P>(4 * q - 2)] = acc[2]; }
-                if (gx + 4 == W) { Y1[rr * P + phys<P>(4 * q + 4)] = acc[2]; Y1[rr * P + phys<P>(4 * q + 5)] = acc[1]; }
             }
         } }
         R2L_SYNC();
