@@ -216,12 +216,10 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             // o_lo < o < o_hi as ONE unsigned compare on the bit patterns (positive floats order like their bits; a
             // negative or NaN o wraps to a huge difference and fails, as it fails the two float compares)
             const unsigned m_base = fbits(o_lo) + 1u, m_span = fbits(o_hi) - m_base;
-            // per-tile bases: channel k of image A / B sits k planes further (32-bit offsets inside an image)
-            const float* goA = a.gout + (size_t)b0 * 3 * plane;
-            const float* goB = a.gout + (size_t)b1 * 3 * plane;
-            const float* yoA = a.out + (size_t)b0 * 3 * plane;
-            const float* yoB = a.out + (size_t)b1 * 3 * plane;
-            const int plane_i = (int)plane;
+            // per-tile bases: channel k sits k planes further, image B 3 planes further (32-bit element offsets inside a pair)
+            const float* goT = a.gout + (size_t)b0 * 3 * plane;
+            const float* yoT = a.out + (size_t)b0 * 3 * plane;
+            const int plane_i = (int)plane, dB = (b1 - b0) * 3 * plane_i;      // image B = image A + dB elements (0: duplicate)
             f2 sg = mk2(0.f, 0.f);                                     // sum G o log2(o), per stream (x gamma when parked)
             // owned rectangle first, halo ring after: whole warps are inside or outside the rectangle that carries
             // the gamma statistic
@@ -240,10 +238,10 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         const int off = k * plane_i + pix;
-                        ga[k] = ld_stream4(goA + off);
-                        ya[k] = ld_stream4(yoA + off);
-                        gb[k] = ld_stream4(goB + off);
-                        yb[k] = ld_stream4(yoB + off);
+                        ga[k] = ld_stream4(goT + off);
+                        ya[k] = ld_stream4(yoT + off);
+                        gb[k] = ld_stream4(goT + (off + dB));
+                        yb[k] = ld_stream4(yoT + (off + dB));
                         ad[k].x = ad[k].y = ad[k].z = ad[k].w = 0.f;
                         if (Cfg::TAIL && a.additive) ad[k] = *reinterpret_cast<const f4*>(a.additive + off);
                     }
