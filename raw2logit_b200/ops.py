@@ -37,7 +37,40 @@ def _ptr(t):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The current CUDA stream of the current device as a cudaStream_t (the raw-handle query: torch.cuda.current_stream()
+    builds a Stream object and costs ~15 us of host time per call, a tenth of the module-path step)."""
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on_device(device):
+    """Device guard for the launch: nothing to switch (the usual case) costs nothing, torch.cuda.device() ~10 us."""
+    return _NO_GUARD if device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+
+_workspaces = {}
+
+
+def _workspace(lib, b, h, w, device):
+    """One scratch buffer per (device, stream), kept for the life of the process: r2l_isp_workspace_bytes is a fixed upper
+    bound, and calls on one stream run in order, so they can share it."""
+    key = (device.index, torch._C._cuda_getCurrentRawStream(device.index))
+    nbytes = lib.r2l_isp_workspace_bytes(b, h, w)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() * 4 < nbytes:
+        buf = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+        _workspaces[key] = buf
+    return buf, nbytes
 
 
 def _raw_input(raw):
@@ -88,7 +121,7 @@ def _forward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, affine,
     lib = _lib.load()
     b, h, w = _check_shape(raw)
     raw, code = _raw_input(raw)
-    with torch.cuda.device(raw.device):
+    with _on_device(raw.device):
         params, keep = _pack_params((bl, wb, ccm, gamma, wd, ws, wg, m1, m2))
         add = None if additive is None else _f32c(additive, 3 * h * w, "additive")
         aff = None if affine is None else _f32c(affine, 6, "affine")
@@ -108,7 +141,7 @@ def _forward_bn_train_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive
     if b * h * w < 2:
         raise ValueError("Expected more than 1 value per channel when training")
     raw, code = _raw_input(raw)
-    with torch.cuda.device(raw.device):
+    with _on_device(raw.device):
         params, keep = _pack_params((bl, wb, ccm, gamma, wd, ws, wg, m1, m2))
         add = None if additive is None else _f32c(additive, 3 * h * w, "additive")
         for t, name in ((running_mean, "running_mean"), (running_var, "running_var")):
@@ -116,8 +149,7 @@ def _forward_bn_train_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive
                 raise TypeError(f"{name} must be a contiguous float32 tensor with 3 elements")
         out = torch.empty((b, 3, h, w), dtype=torch.float32, device=raw.device)
         saved = torch.empty(6, dtype=torch.float32, device=raw.device)
-        nbytes = lib.r2l_isp_workspace_bytes(b, h, w)
-        ws_buf = torch.empty(nbytes // 4, dtype=torch.float32, device=raw.device)
+        ws_buf, nbytes = _workspace(lib, b, h, w, raw.device)
         luma = _luma_buffer(lib, raw, code, b, h, w, out, add, save_luma)
         rc = lib.r2l_isp_forward_bn_train(_ptr(raw), code, raw_denominator, b, h, w, ctypes.byref(params), _ptr(add),
                                           _ptr(out), _ptr(running_mean), _ptr(running_var), momentum, eps,
@@ -130,13 +162,12 @@ def _forward_bn_train_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive
 def _bn_backward_prepare_cuda(grad_out, out, saved_affine):
     lib = _lib.load()
     b, _, h, w = out.shape
-    with torch.cuda.device(out.device):
+    with _on_device(out.device):
         g = _f32c(grad_out, out.numel(), "grad_out")
         y = _f32c(out, out.numel(), "out")
         sa = _f32c(saved_affine, 6, "saved_affine")
         tail = torch.empty(15, dtype=torch.float32, device=out.device)
-        nbytes = lib.r2l_isp_workspace_bytes(b, h, w)
-        ws_buf = torch.empty(nbytes // 4, dtype=torch.float32, device=out.device)
+        ws_buf, nbytes = _workspace(lib, b, h, w, out.device)
         rc = lib.r2l_isp_bn_backward_prepare(_ptr(g), _ptr(y), _ptr(sa), b, h, w, _ptr(tail), _ptr(ws_buf), nbytes,
                                              _stream())
     _lib.check(rc, "r2l_isp_bn_backward_prepare")
@@ -148,7 +179,7 @@ def _backward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, grad_t
     lib = _lib.load()
     b, h, w = _check_shape(raw)
     raw, code = _raw_input(raw)
-    with torch.cuda.device(raw.device):
+    with _on_device(raw.device):
         params, keep = _pack_params((bl, wb, ccm, gamma, wd, ws, wg, m1, m2))
         g = _f32c(grad_out, b * 3 * h * w, "grad_out")
         gs = None if grad_tail is None else _f32c(grad_tail, 15, "grad_tail")
@@ -159,8 +190,7 @@ def _backward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, grad_t
             lum = _f32c(luma, lib.r2l_isp_saved_luma_floats(b, h, w), "luma")
         graw = torch.empty((b, h, w), dtype=torch.float32, device=raw.device) if need_raw_grad else None
         gpar = torch.empty(_lib.NUM_PARAM_GRADS, dtype=torch.float32, device=raw.device)
-        nbytes = lib.r2l_isp_workspace_bytes(b, h, w)
-        ws_buf = torch.empty(nbytes // 4, dtype=torch.float32, device=raw.device)
+        ws_buf, nbytes = _workspace(lib, b, h, w, raw.device)
         rc = lib.r2l_isp_backward(_ptr(raw), code, raw_denominator, b, h, w, ctypes.byref(params), _ptr(g), _ptr(gs),
                                   _ptr(add), _ptr(y), _ptr(lum), _ptr(graw), _ptr(gpar), _ptr(ws_buf), nbytes, _stream())
     _lib.check(rc, "r2l_isp_backward")
@@ -180,7 +210,7 @@ def _mosaic_cuda(raw, black_level, reduce_size, out_channels, raw_denominator):
         raise RuntimeError(f"The expanded size of the tensor must match the existing size: odd H={h} or W={w} "
                            "with reduce_size=True")
     raw, code = _raw_input(raw)
-    with torch.cuda.device(raw.device):
+    with _on_device(raw.device):
         bl = None if black_level is None else _f32c(black_level, 4, "black_level")
         shape = (b, out_channels, h // 2, w // 2) if reduce_size else (b, out_channels, h, w)
         out = torch.empty(shape, dtype=torch.float32, device=raw.device)
@@ -193,7 +223,7 @@ def _mosaic_cuda(raw, black_level, reduce_size, out_channels, raw_denominator):
 def _mosaic_backward_cuda(grad_out, h, w, reduce_size, out_channels):
     lib = _lib.load()
     b = grad_out.shape[0]
-    with torch.cuda.device(grad_out.device):
+    with _on_device(grad_out.device):
         g = _f32c(grad_out, grad_out.numel(), "grad_out")
         graw = torch.empty((b, h, w), dtype=torch.float32, device=g.device)
         rc = lib.r2l_isp_mosaic_backward(_ptr(g), b, h, w, int(reduce_size), out_channels, _ptr(graw), _stream())
@@ -205,7 +235,7 @@ def _batch_sum_cuda(x, scale):
     lib = _lib.load()
     b, c = x.shape[0], x.shape[1]
     hw = x.numel() // max(b * c, 1)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         xc = _f32c(x, x.numel(), "x")
         sc = None if scale is None else _f32c(scale, c, "scale")
         out = torch.empty((1,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)

@@ -173,8 +173,9 @@ class ParametrizedProcessing(nn.Module):
     def forward(self, raw):
         assert raw.ndim == 3, f"needs dims (B, H, W), got {raw.shape}"
         _require_cuda(raw)
-        self.stages = {}
-        self.buffer = {}
+        d = self.__dict__                      # plain attributes: nn.Module.__setattr__ costs ~10 us per assignment
+        d['stages'] = {}
+        d['buffer'] = {}
         if self.track_stages:
             return self._forward_staged(raw)
 
