@@ -67,24 +67,57 @@ __global__ void affine_inplace_kernel(float* x, const float* affine, int BC, int
     }
 }
 
-// backward of the batch statistics: per channel sum(gy), sum(gy*y) with y the normalised output
-constexpr int kBnBwdBlocks = 128;
-__global__ void __launch_bounds__(256) bn_backward_stats_kernel(const float* gy, const float* y, int B, int HW,
-                                                                float* partials /* [3][kBnBwdBlocks][2] */) {
+// backward of the batch statistics: per channel sum(gy), sum(gy*y) with y the normalised output.
+// A pure streaming reduction over 24 B/px: 128-bit loads, four independent accumulator pairs per thread (eight loads in
+// flight), two CTAs per SM and channel.  (The first version -- scalar loads into one dependent accumulator chain, 128
+// CTAs per channel -- ran at 1.4 TB/s: 69.6 us for 64 x 256 x 256, more than the fused forward kernel.)
+constexpr int kBnBwdBlocks = 296;
+template <bool VEC>
+__global__ void __launch_bounds__(256) bn_backward_stats_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                                                int B, int HW, float* partials /* [3][kBnBwdBlocks][2] */) {
     const int c = blockIdx.y;
-    float s1 = 0.f, s2 = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const size_t base = ((size_t)b * 3 + c) * HW;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-            const float g = gy[base + i];
-            s1 += g;
-            s2 = fmaf(g, y[base + i], s2);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (VEC) {                                          // HW % 4 == 0, 16-byte aligned tensors, B * HW / 4 < 2^31
+        // the (image, position) space of this channel, flattened, is cut into one contiguous chunk per CTA, so every
+        // CTA has work whatever the plane size (a grid-stride loop inside each plane left 3/4 of the CTAs idle at 256^2)
+        const int n4 = HW >> 2, total = B * n4;
+        const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int l0 = blockIdx.x * per, l1 = min(total, l0 + per);
+        const float4* g4 = reinterpret_cast<const float4*>(gy);
+        const float4* y4 = reinterpret_cast<const float4*>(y);
+        for (int l = l0 + threadIdx.x; l < l1; l += 4 * 256) {
+            float4 g[4], v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int lu = l + u * 256;
+                g[u] = make_float4(0.f, 0.f, 0.f, 0.f); v[u] = g[u];
+                if (lu < l1) {
+                    const int b = lu / n4, i = lu - b * n4;
+                    const size_t at = ((size_t)b * 3 + c) * n4 + i;
+                    g[u] = g4[at]; v[u] = y4[at];              // default cache policy: the fused backward re-reads both from L2
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s1[u] += (g[u].x + g[u].y) + (g[u].z + g[u].w);
+                s2[u] = fmaf(g[u].x, v[u].x, fmaf(g[u].y, v[u].y, fmaf(g[u].z, v[u].z, fmaf(g[u].w, v[u].w, s2[u]))));
+            }
+        }
+    } else {
+        for (int b = 0; b < B; ++b) {
+            const size_t base = ((size_t)b * 3 + c) * HW;
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+                const float g = gy[base + i];
+                s1[0] += g;
+                s2[0] = fmaf(g, y[base + i], s2[0]);
+            }
         }
     }
+    float t1 = (s1[0] + s1[1]) + (s1[2] + s1[3]), t2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
     __shared__ float red[2][8];
-    s1 = warp_sum_all(s1); s2 = warp_sum_all(s2);
+    t1 = warp_sum_all(t1); t2 = warp_sum_all(t2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+    if (lane == 0) { red[0][warp] = t1; red[1][warp] = t2; }
     __syncthreads();
     if (threadIdx.x < 2) {
         float t = 0.f;
@@ -533,7 +566,10 @@ int r2l_isp_bn_backward_prepare(const float* grad_out, const float* out, const f
     if (workspace_bytes < (size_t)3 * kBnBwdBlocks * 2 * sizeof(float)) return R2L_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* partials = static_cast<float*>(workspace);
-    bn_backward_stats_kernel<<<dim3(kBnBwdBlocks, 3), 256, 0, st>>>(grad_out, out, B, H * W, partials);
+    if (((H * W) & 3) == 0 && aligned(grad_out, 16) && aligned(out, 16) && (size_t)B * H * W / 4 < ((size_t)1 << 31) - 1024)
+        bn_backward_stats_kernel<true><<<dim3(kBnBwdBlocks, 3), 256, 0, st>>>(grad_out, out, B, H * W, partials);
+    else
+        bn_backward_stats_kernel<false><<<dim3(kBnBwdBlocks, 3), 256, 0, st>>>(grad_out, out, B, H * W, partials);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
     bn_backward_finish_kernel<<<1, 96, 0, st>>>(partials, saved_affine, (double)B * H * W, grad_tail);
