@@ -53,12 +53,16 @@ R2L_HD f2 pack2(float x, float y, float one) { return mul2s(mk2(x, y), one); }
 #ifdef R2L_HOST_EMU
 #define R2L_ANY(x) (x)
 #define R2L_PARK_LOAD(N, col, v)  { const float* s_ = accs[tid].sums + (col); for (int i_ = 0; i_ < (N); ++i_) (v)[i_] = s_[i_]; }
+#define R2L_PARK_READY(N, v)
 #define R2L_PARK_STORE(N, col, v) { float* s_ = accs[tid].sums + (col); for (int i_ = 0; i_ < (N); ++i_) s_[i_] = (v)[i_]; }
 struct Bwd5Acc { float sums[kBwd5AccFloats]; };
 #else
 #define R2L_ANY(x) (__any_sync(0xffffffffu, (x)) != 0)
-#define R2L_PARK_LOAD(N, col, v)  { __syncwarp(); tmem::load<N>(tacc + (col), v); tmem::wait_ld(); }
-#define R2L_PARK_STORE(N, col, v) { __syncwarp(); tmem::store<N>(tacc + (col), v); tmem::wait_st(); }
+// LOAD only requests (after the thread's earlier stores have landed); the values are needed when the phase ends, so the
+// TMEM round trip runs behind the phase's arithmetic and READY (wait + register tie) sits in front of their first use
+#define R2L_PARK_LOAD(N, col, v)  { __syncwarp(); tmem::wait_st(); tmem::load<N>(tacc + (col), v); }
+#define R2L_PARK_READY(N, v)      { tmem::ready<N>(v); }
+#define R2L_PARK_STORE(N, col, v) { __syncwarp(); tmem::store<N>(tacc + (col), v); }
 #endif
 
 #ifndef R2L_HOST_EMU
@@ -287,6 +291,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             {
                 float v[2];
                 R2L_PARK_LOAD(2, kB5Sg, v)
+                R2L_PARK_READY(2, v)
                 v[0] = fmaf_(sg.x, gam, v[0]);
                 if (!dup) v[1] = fmaf_(sg.y, gam, v[1]);
                 R2L_PARK_STORE(2, kB5Sg, v)
@@ -381,6 +386,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     for (int bb = 0; bb < 5; ++bb) { acc[bb] = mk2(0.f, 0.f); w5[bb] = wg[A * 5 + bb]; }
 #pragma unroll
                     for (int u = 0; u < NI5; ++u) full(u, 4 - A, w5, acc);
+                    R2L_PARK_READY(5, wa)
 #pragma unroll
                     for (int bb = 0; bb < 5; ++bb) wa[bb] += acc[bb].x + acc[bb].y;
                     R2L_PARK_STORE(5, kB5Wg + 5 * A, wa)
@@ -404,6 +410,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                                         : A == 3 ? (t == 3 ? 3 : -1) : (t == 3 ? 2 : (t == 4 ? 4 : -1));
                             if (d >= 0) full(u, d, w5, acc);
                         }
+                        R2L_PARK_READY(5, wa)
 #pragma unroll
                         for (int bb = 0; bb < 5; ++bb) wa[bb] += acc[bb].x + acc[bb].y;
                         R2L_PARK_STORE(5, kB5Wg + 5 * A, wa)
@@ -465,13 +472,11 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
             float ws[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) ws[t] = T->Ws[t];
-            f2 ws2[9];                                                 // packed (image A, image B) dWs sums
-            {
-                float wa[9];
-                R2L_PARK_LOAD(9, kB5Ws, wa)
+            f2 ws2[9];                                                 // packed (image A, image B) dWs sums of this tile
+            float wspark[9];
+            R2L_PARK_LOAD(9, kB5Ws, wspark)
 #pragma unroll
-                for (int t = 0; t < 9; ++t) ws2[t] = mk2(wa[t], 0.f);
-            }
+            for (int t = 0; t < 9; ++t) ws2[t] = mk2(0.f, 0.f);
 #ifdef R2L_HOST_EMU
             f2 c6[NI6][2][4];
             load_c6(tid, c6);
@@ -527,12 +532,10 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 region_item<TH, G, 1>(item, r, g);
                 b6(std::integral_constant<int, 1>(), r, g, false, nullptr);
             }
-            {
-                float wa[9];
+            R2L_PARK_READY(9, wspark)
 #pragma unroll
-                for (int t = 0; t < 9; ++t) wa[t] = ws2[t].x + ws2[t].y;
-                R2L_PARK_STORE(9, kB5Ws, wa)
-            }
+            for (int t = 0; t < 9; ++t) wspark[t] += ws2[t].x + ws2[t].y;
+            R2L_PARK_STORE(9, kB5Ws, wspark)
 #ifndef R2L_HOST_EMU
             load_x7(tid, xa7, xb7);
 #endif
@@ -632,6 +635,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                         for (int bb = 0; bb < 3; ++bb) { acc[cp][bb] = mk2(0.f, 0.f); w[cp][bb] = awq[cp * 27 + A * 3 + bb]; }
 #pragma unroll
                     for (int u = 0; u < NI; ++u) full(u, pl, 2 - A, w, acc);
+                    if (A == 1) { R2L_PARK_READY(8, qa) } else { R2L_PARK_READY(6, qa) }
 #pragma unroll
                     for (int cp = 0; cp < 2; ++cp)
 #pragma unroll
@@ -670,6 +674,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
                         for (int u = 0; u < NI; ++u)
                             if (live[u] && (A == 0 ? f_top[u] : f_bot[u])) full(u, pl, A, w, acc);
+                        R2L_PARK_READY(6, qa)
 #pragma unroll
                         for (int cp = 0; cp < 2; ++cp)
 #pragma unroll
@@ -718,9 +723,10 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         for (int grp = 0; grp < 3; ++grp) {
             float v[32];
             __syncwarp();
+            tmem::wait_st();
             tmem::load<16>(tacc + grp * 32, v);
             tmem::load<16>(tacc + grp * 32 + 16, v + 16);
-            tmem::wait_ld();
+            tmem::ready<32>(v);
             red[warp * RP + grp * 32 + lane] = warp_transpose_sum32(v);
         }
         tmem::fence_before_sync();

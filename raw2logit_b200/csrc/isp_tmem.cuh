@@ -94,7 +94,7 @@ __device__ __forceinline__ void st16(uint32_t a, const float* v) {
 #undef R2L_U
 
 // N consecutive columns <-> v[0..N), split into power-of-two pieces (all indices compile-time after unrolling).
-// The caller waits (wait_ld before the first use of v, wait_st before the columns are read again).
+// The caller waits (ready<N>(v) before the first use of v, wait_st before the columns are read again).
 template <int N> __device__ __forceinline__ void load(uint32_t a, float* v) {
     static_assert(N >= 0 && N < 64, "pieces up to 16 columns");
     if constexpr (N >= 16) { ld16(a, v); load<N - 16>(a + 16, v + 16); }
@@ -102,6 +102,14 @@ template <int N> __device__ __forceinline__ void load(uint32_t a, float* v) {
     else if constexpr (N >= 4) { ld4(a, v); load<N - 4>(a + 4, v + 4); }
     else if constexpr (N >= 2) { ld2(a, v); load<N - 2>(a + 2, v + 2); }
     else if constexpr (N >= 1) { ld1(a, v); }
+}
+// Wait for every tcgen05.ld of this thread and tie v[0..N) to the wait: the compiler only sees register outputs of the
+// load instructions, not that they are filled asynchronously, so without the (empty, ordered) asm statements below it
+// would be free to move a use of v above the wait.
+template <int N> __device__ __forceinline__ void ready(float* v) {
+    wait_ld();
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("" : "+f"(v[i]));
 }
 template <int N> __device__ __forceinline__ void store(uint32_t a, const float* v) {
     static_assert(N >= 0 && N < 64, "pieces up to 16 columns");
