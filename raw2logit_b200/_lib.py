@@ -48,7 +48,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
+    path = os.environ.get("R2L_ISP_LIB") or _build.LIB_PATH      # R2L_ISP_LIB: another build of the same ABI (A/B timing)
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is missing: the raw2logit_b200 CUDA library has not been built. "
