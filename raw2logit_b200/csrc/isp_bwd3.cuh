@@ -47,12 +47,14 @@ R2L_HD f2 mul2vv(f2 a, f2 b) {
 }
 
 
-// read-once global data (grad_out): streaming 128-bit load
+// read-once global data (grad_out, forward output, luma planes, raw centres): 128-bit load
 R2L_HD f4 ld_stream4(const float* p) {
 #ifdef R2L_HOST_EMU
     f4 v; v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3]; return v;
 #else
-    return __ldcs(reinterpret_cast<const float4*>(p));
+    // L2-only (ld.global.cg): the data is used once per CTA, the halo is re-read by neighbouring CTAs from L2.  Measured
+    // on the fifth-generation backward (in-call A/B, 64 x 256 x 256): .cg 89.4 us, .cs (evict-first) 90.7 us, default 90.5 us
+    return __ldcg(reinterpret_cast<const float4*>(p));
 #endif
 }
 
