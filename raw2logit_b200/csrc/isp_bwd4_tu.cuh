@@ -35,9 +35,6 @@ static int launch_backward4_impl(const BwdArgs& a, cudaStream_t st, int* grid_us
         return kNotServed;                                                          // 128-bit rows
     const bool tail = a.gtail != nullptr;
     constexpr int CPS = kBwd4CtasPerSm;
-    if (const char* v = getenv("R2L_BWD4_VARIANT")) {            // tuning experiment: one CTA of 256 threads per SM
-        if (v[0] == '1' && a.graw && !tail) return launch_backward4_t<Bwd4Cfg<32, 64, 256, true, false>, RawT, 1>(a, st, grid_used);
-    }
     if (a.graw) return tail ? launch_backward4_t<Bwd4<true, true>, RawT, CPS>(a, st, grid_used)
                             : launch_backward4_t<Bwd4<true, false>, RawT, CPS>(a, st, grid_used);
     return tail ? launch_backward4_t<Bwd4<false, true>, RawT, CPS>(a, st, grid_used)
