@@ -4,13 +4,17 @@
 // adjoint algebra as the fourth generation (isp_bwd4.cuh: nothing recomputed, forward output + saved luma planes), but
 // the 96 per-thread running sums behind the 132 parameter gradients no longer occupy registers for the whole launch:
 //   * they are parked in TMEM (isp_tmem.cuh: one private 32-bit cell per thread and column) and a phase loads only the
-//     group it updates -- B4 the gamma sum, B5 the 25 Gaussian taps, B6 the 9 sharpening taps, B7 one YUV channel's
-//     20 demosaic sums at a time -- and stores it back when it ends;
-//   * with at most 36 sums live, the kernel fits 128 registers: 256 threads x 2 CTAs per SM = 16 warps (was 8 at
-//     255 registers with spills, profiles/r01_v4_summary.md), so the global loads of one warp hide behind the
+//     group it updates -- B4 the gamma sum, B5 five sums per Gaussian tap row, B6 the 9 sharpening taps, B7 six sums per
+//     gradient plane and tap row -- and stores it back when the pass ends; the load is requested when the pass starts
+//     and awaited at its end, where the sums of the tile are added;
+//   * with at most a dozen packed sums live, the kernel fits 128 registers: 256 threads x 2 CTAs per SM = 16 warps (was
+//     8 at 255 registers with spills, profiles/r01_v4_summary.md), so the global loads of one warp hide behind the
 //     stencils of three others;
-//   * B7 walks the three gradient planes one after the other (k outermost) with packed (image A, image B)
-//     accumulators: the Q' statistic is one FFMA2 per tap and site pair instead of two scalar FMAs;
+//   * every statistic is accumulated in packed (image A, image B) registers: one FFMA2 per tap and site pair (the Q'
+//     statistic took two scalar FMAs); B7 walks the three gradient planes one after the other (k outermost);
+//   * the hot loops are straight-line code: pad columns are realised as per-site weights and masked centres, pad rows
+//     in a cold pass behind a warp vote, plane / tap-row loops are runtime loops (the kernel fits the instruction cache);
+//   * the centre values a phase reads from global memory are requested ahead of the CTA barrier before it;
 //   * stencil weights are read from shared memory next to their use (uniform-address LDS) instead of sitting in
 //     25 / 54 registers for a whole phase;
 //   * no software L2 prefetch: prefetch.global.L2 (CCTL.E.PF2) fetches one 32-byte sector per instruction, and both the
