@@ -319,7 +319,7 @@ def run_ours(args):
             out.backward(gouts[i % S])
             consumed[i % 2].record(main)
             flat = torch.cat([p.grad.reshape(-1) for p in plist])
-            if world > 1:
+            if world > 1 and not fused_e2e:
                 dist.all_reduce(flat)
             host_grads.copy_(flat, non_blocking=True)
             for p in plist:
@@ -342,11 +342,19 @@ def run_ours(args):
             ms = t.item()
         return world * pix / (ms / steps * 1e-3) / 1e6, steps
 
+    # N > 1: the module path exchanges the ISP gradients inside its backward kernel too (parallel.enable_fused_...)
+    fused_e2e = False
+    if xch is not None:
+        from raw2logit_b200 import parallel
+        parallel.enable_fused_gradient_exchange(average=False)
+        fused_e2e = True
     e2e_value, e2e_steps = e2e_measure(host_raw)
     # same step fed with the sensor's uint16 words (2 B/px over PCIe; the divide by 2^16-1 happens in the kernel,
     # dataset.py:87); parameter gradients only -- an integer input has no gradient
     host_u16 = [syn.to_uint16(h).pin_memory() for h in host_raw]
     e2e_u16_value, _ = e2e_measure(host_u16)
+    if fused_e2e:
+        parallel.disable_fused_gradient_exchange()
 
     if rank != 0:
         if world > 1:
@@ -367,7 +375,10 @@ def run_ours(args):
             "(r2l_isp_backward_dp)" if xch is not None else "NCCL all-reduce of the 132 gradients after the backward")),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pix * 4, "d2h_bytes_per_step": 132 * 4,
                 "steps": e2e_steps, "api": "ParametrizedProcessing.forward + autograd backward; fp32 raw batch copied "
-                                           "from pinned host memory every step on a prefetch stream (double-buffered)"},
+                                           "from pinned host memory every step on a prefetch stream (double-buffered)"
+                                           + ("; gradients exchanged inside the backward kernel "
+                                              "(parallel.enable_fused_gradient_exchange)" if fused_e2e else
+                                              ("; NCCL all-reduce of the gradients" if world > 1 else ""))},
         "e2e_uint16": {"value": e2e_u16_value, "unit": UNIT, "h2d_bytes_per_step": pix * 2, "d2h_bytes_per_step": 132 * 4,
                        "note": "same step with uint16 raw words over PCIe (normalised in the kernel); parameter "
                                "gradients only"},

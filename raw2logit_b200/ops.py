@@ -60,6 +60,18 @@ def _on_device(device):
 
 _workspaces = {}
 
+# data-parallel gradient exchange fused into the backward kernel (set by parallel.enable_fused_gradient_exchange)
+_exchange = None
+_exchange_average = True
+
+
+def set_gradient_exchange(exchange, average=True):
+    """``exchange``: a ``parallel.PeerExchange`` (every later fused backward on this process sums / averages its 132
+    parameter gradients over the ranks inside the kernel) or None (local gradients).  Every rank must run the same
+    sequence of backward calls while it is set."""
+    global _exchange, _exchange_average
+    _exchange, _exchange_average = exchange, bool(average)
+
 
 def _workspace(lib, b, h, w, device):
     """One scratch buffer per (device, stream), kept for the life of the process: r2l_isp_workspace_bytes is a fixed upper
@@ -191,8 +203,19 @@ def _backward_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, grad_out, grad_t
         graw = torch.empty((b, h, w), dtype=torch.float32, device=raw.device) if need_raw_grad else None
         gpar = torch.empty(_lib.NUM_PARAM_GRADS, dtype=torch.float32, device=raw.device)
         ws_buf, nbytes = _workspace(lib, b, h, w, raw.device)
-        rc = lib.r2l_isp_backward(_ptr(raw), code, raw_denominator, b, h, w, ctypes.byref(params), _ptr(g), _ptr(gs),
-                                  _ptr(add), _ptr(y), _ptr(lum), _ptr(graw), _ptr(gpar), _ptr(ws_buf), nbytes, _stream())
+        if _exchange is not None:
+            # data-parallel: the 132 gradients leave the kernel already reduced over the ranks (parallel.PeerExchange)
+            if y is None or lum is None:
+                raise RuntimeError("the fused gradient exchange needs the saved output and luma planes (unset "
+                                   "R2L_ISP_RECOMPUTE / R2L_ISP_NO_LUMA, shapes with W % 4 == 0)")
+            desc = _exchange.next(average=_exchange_average)
+            rc = lib.r2l_isp_backward_dp(_ptr(raw), code, raw_denominator, b, h, w, ctypes.byref(params), _ptr(g),
+                                         _ptr(gs), _ptr(add), _ptr(y), _ptr(lum), _ptr(graw), _ptr(gpar), _ptr(ws_buf),
+                                         nbytes, ctypes.byref(desc), _stream())
+        else:
+            rc = lib.r2l_isp_backward(_ptr(raw), code, raw_denominator, b, h, w, ctypes.byref(params), _ptr(g), _ptr(gs),
+                                      _ptr(add), _ptr(y), _ptr(lum), _ptr(graw), _ptr(gpar), _ptr(ws_buf), nbytes,
+                                      _stream())
     _lib.check(rc, "r2l_isp_backward")
     if graw is None:
         graw = torch.empty(0, dtype=torch.float32, device=raw.device)

@@ -96,3 +96,20 @@ class PeerExchange:
         from . import _lib
         self.epoch += 1
         return _lib.IspAllreduce(self.world, self.rank, self.peers, self.epoch, 1.0 / self.world if average else 1.0)
+
+
+def enable_fused_gradient_exchange(group=None, average=True):
+    """From now on the ISP's fused backward (module API: ``ParametrizedProcessing`` under autograd) returns parameter
+    gradients that are already summed (``average=False``) or averaged over the ranks of ``group``: the exchange runs
+    inside the backward kernel (``PeerExchange``).  All-reduce only the *other* parameters afterwards, e.g.
+    ``allreduce_gradients(task_model.parameters())``.  Every rank must run the same sequence of ISP backward calls.
+    Returns the ``PeerExchange``; ``disable_fused_gradient_exchange()`` restores local gradients."""
+    from . import ops
+    exchange = PeerExchange(group)
+    ops.set_gradient_exchange(exchange, average)
+    return exchange
+
+
+def disable_fused_gradient_exchange():
+    from . import ops
+    ops.set_gradient_exchange(None)

@@ -62,6 +62,30 @@ def main():
             gathered = [torch.empty_like(g_dp) for _ in range(world)]
             dist.all_gather(gathered, g_dp)
             assert all(torch.equal(gathered[0], g) for g in gathered), "ranks disagree bitwise"
+    # the same through the module API: autograd backward with the exchange enabled == local gradients + NCCL average
+    raw = syn.smooth_scene(4, 128, 192, "drone", seed=900 + rank).to(dev)
+    gout = torch.randn(4, 3, 128, 192, device=dev, generator=torch.Generator(dev).manual_seed(70 + rank)) / raw.numel()
+    plist = list(mod.parameters())
+
+    def grads():
+        for p in plist:
+            p.grad = None
+        x = raw.clone().requires_grad_(True)
+        mod(x).backward(gout)
+        return torch.cat([p.grad.reshape(-1) for p in plist]), x.grad
+
+    g_local, gx_local = grads()
+    dist.all_reduce(g_local)
+    g_local /= world
+    parallel.enable_fused_gradient_exchange(average=True)
+    for rep in range(2):
+        g_fused, gx_fused = grads()
+        torch.cuda.synchronize()
+        err = (g_fused - g_local).abs().max().item() / max(1.0, g_local.abs().max().item())
+        worst = max(worst, err)
+        assert err <= 1e-5, ("module API", rep, err)
+        assert torch.equal(gx_fused, gx_local), "the raw gradient must stay local"
+    parallel.disable_fused_gradient_exchange()
     if rank == 0:
         print(f"dp_check ok: world {world}, worst relative error vs NCCL {worst:.2e}, ranks bit-identical", flush=True)
     dist.destroy_process_group()

@@ -36,3 +36,15 @@ def test_fused_exchange_matches_nccl_on_two_gpus():
            "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "scripts", "dp_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0 and "dp_check ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_module_path_switch_is_explicit():
+    """The module path only uses the fused exchange after parallel.enable_fused_gradient_exchange(); the switch is a
+    plain process-wide setting that can be cleared again (no GPU needed to check the plumbing)."""
+    from raw2logit_b200 import ops, parallel
+    assert ops._exchange is None
+    marker = object()
+    ops.set_gradient_exchange(marker, average=False)
+    assert ops._exchange is marker and ops._exchange_average is False
+    parallel.disable_fused_gradient_exchange()
+    assert ops._exchange is None
