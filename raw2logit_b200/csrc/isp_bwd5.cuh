@@ -71,37 +71,57 @@ struct Bwd5Acc { float sums[kBwd5AccFloats]; };
 
 #ifndef R2L_HOST_EMU
 // ---- one-shot all-reduce of the 132 gradients over NVLink peer memory, run by the CTA that finished them ------------
-// (r2l_isp_backward_dp, include/r2l_isp.h).  Every gradient travels as one 8-byte word {value, epoch}: an aligned
-// 64-bit store is single-copy atomic, so the epoch tag tells the reader that the value next to it is this step's -- no
+// (r2l_isp_backward_dp, include/r2l_isp.h).  Every gradient travels as one 8-byte word {value, epoch} written by ONE
+// 64-bit store (single-copy atomic), so the epoch tag tells the reader that the value next to it is this step's -- no
 // fence, no separate flag, one NVLink one-way latency.  Push: thread e writes word e of this rank's slot on EVERY rank.
 // Pull: thread e polls word e of every rank's slot in OUR buffer until it carries the epoch and adds the values in
 // rank order -- the same order everywhere, so all ranks hold bit-identical sums.  Slots are double-buffered by epoch
 // parity: a rank that already pushes step i + 1 cannot overwrite what a slower rank still reads for step i, and it
 // cannot reach step i + 2 before that rank has pushed step i + 1.
 __device__ __forceinline__ void st_tagged_sys(float* p, float v, unsigned tag) {
-    asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+    // ONE 64-bit store: {value (low word), epoch tag (high word)} -- single-copy atomic, unlike a .v2.b32 access, which
+    // the PTX memory model treats as two scalar accesses in unspecified order
+    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-__device__ __forceinline__ float ld_tagged_sys(const float* p, unsigned tag) {
-    unsigned v, t;
-    do {
-        asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(p) : "memory");
-    } while (t != tag);
-    return __uint_as_float(v);
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
+// polls until the word carries `tag`; gives up at `deadline` (a peer that crashed or skipped its backward must not hang
+// the GPU): then *ok is cleared and the caller poisons the gradients with NaN, which the host sees in the result
+__device__ __forceinline__ float ld_tagged_sys(const float* p, unsigned tag, unsigned long long deadline, bool* ok) {
+    unsigned long long w;
+    unsigned spins = 0;
+    for (;;) {
+        asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+        if ((unsigned)(w >> 32) == tag) break;
+        if ((++spins & 1023u) == 0u && global_timer_ns() > deadline) { *ok = false; break; }
+    }
+    return __uint_as_float((unsigned)w);
+}
+constexpr unsigned long long kExchangeTimeoutNs = 5000000000ull;        // 5 s
 template <int NT> __device__ __forceinline__ void peer_allreduce(const BwdArgs& a) {
     static_assert(kSlotPitch >= R2L_NUM_PARAM_GRADS, "one tagged word per gradient");
-    const int world = a.world, tid = threadIdx.x;
+    static_assert(NT >= R2L_NUM_PARAM_GRADS, "thread e owns gradient e from its local read to its final write");
+    const int world = a.world, e = threadIdx.x;
     const size_t slot0 = (size_t)(a.epoch & 1u) * world * (2 * kSlotPitch);      // floats; a slot = kSlotPitch words of 8 bytes
     __syncthreads();                                                     // a.grads of this launch are written
-    for (int i = tid; i < world * R2L_NUM_PARAM_GRADS; i += NT) {
-        const int p = i / R2L_NUM_PARAM_GRADS, e = i - p * R2L_NUM_PARAM_GRADS;
-        st_tagged_sys(a.peers[p] + slot0 + (size_t)a.rank * (2 * kSlotPitch) + 2 * e, a.grads[e], a.epoch);
-    }
-    const float* mine = a.peers[a.rank] + slot0;
-    for (int e = tid; e < R2L_NUM_PARAM_GRADS; e += NT) {
+    if (e < R2L_NUM_PARAM_GRADS) {
+        // Thread e is the only one that touches a.grads[e] from here on: it reads the local value once, pushes it to
+        // every rank, then pulls every rank's word e and writes the sum back.  (A version whose push loop ran over
+        // (rank, gradient) pairs let another thread push a.grads[e] after thread e had already overwritten it with
+        // the reduced sum -- ADVICE round 1.)
+        const float local = a.grads[e];
+        for (int p = 0; p < world; ++p)
+            st_tagged_sys(a.peers[p] + slot0 + (size_t)a.rank * (2 * kSlotPitch) + 2 * e, local, a.epoch);
+        const float* mine = a.peers[a.rank] + slot0;
+        const unsigned long long deadline = global_timer_ns() + kExchangeTimeoutNs;
+        bool ok = true;
         float sum = 0.f;
-        for (int r = 0; r < world; ++r) sum += ld_tagged_sys(mine + (size_t)r * (2 * kSlotPitch) + 2 * e, a.epoch);
-        a.grads[e] = sum * a.dp_scale;
+        for (int r = 0; r < world; ++r) sum += ld_tagged_sys(mine + (size_t)r * (2 * kSlotPitch) + 2 * e, a.epoch, deadline, &ok);
+        a.grads[e] = ok ? sum * a.dp_scale : __int_as_float(0x7fc00000);
     }
 }
 #endif

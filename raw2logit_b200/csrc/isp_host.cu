@@ -445,19 +445,14 @@ static int launch_backward_any(const BwdArgs& a, int raw_dtype, float* grads, cu
     int rc = kNotServed;
     const char* force = getenv("R2L_ISP_FORCE_GENERIC");        // debugging knob
     if (a.world > 1) {                                          // the fused exchange lives in the fifth generation only
-        const char* gen = getenv("R2L_ISP_BWD_GEN");
-        if ((force && force[0] == '1') || (gen && gen[0] == '4') || !(a.out && a.luma)) return R2L_ERR_BAD_ARGUMENT;
+        if ((force && force[0] == '1') || !(a.out && a.luma)) return R2L_ERR_BAD_ARGUMENT;
     }
     if (!(force && force[0] == '1')) {
         if (a.out && a.luma) {                                  // fourth / fifth generation: nothing recomputed, fused finish
             BwdArgs a4 = a;
             a4.grads = grads;
             a4.ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.partials) + kTicketOffset);
-            const char* gen = getenv("R2L_ISP_BWD_GEN");            // debugging knob: 4 = registers-only predecessor
-            if (gen && gen[0] == '4')
-                rc = raw_dtype == R2L_F32 ? launch_backward4_f32(a4, st, &g) : launch_backward4_u16(a4, st, &g);
-            else
-                rc = raw_dtype == R2L_F32 ? launch_backward5_f32(a4, st, &g) : launch_backward5_u16(a4, st, &g);
+            rc = raw_dtype == R2L_F32 ? launch_backward5_f32(a4, st, &g) : launch_backward5_u16(a4, st, &g);
             if (rc == R2L_OK) return rc;
         }
         if (a.world > 1) return rc == kNotServed ? (int)R2L_ERR_BAD_ARGUMENT : rc;   // the exchange lives in that kernel only

@@ -44,10 +44,7 @@ int launch_forward_u16(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_
 // third-generation backward (TMA-fed); returns kNotServed when the shape / alignment is not served
 int launch_backward3_f32(const BwdArgs& a, cudaStream_t st, int* grid_used);
 int launch_backward3_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
-// fourth-generation backward (forward output + saved luma planes, fused finish when a.ticket is set)
-int launch_backward4_f32(const BwdArgs& a, cudaStream_t st, int* grid_used);
-int launch_backward4_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
-// fifth-generation backward (the fourth with its running sums in tensor memory)
+// fifth-generation backward (forward output + saved luma planes, running sums in tensor memory, fused finish)
 int launch_backward5_f32(const BwdArgs& a, cudaStream_t st, int* grid_used);
 int launch_backward5_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
 // generic scalar kernels: any shape, any alignment

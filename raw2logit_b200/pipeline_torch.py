@@ -84,40 +84,14 @@ class RawToRGB(nn.Module):
 
 
 class NNProcessing(nn.Module):
-    """Learned U-Net++ processor (reference ``NNProcessing``, pipeline_torch.py:83-126).  Out of the hot-path scope:
-    it is a CNN from ``segmentation_models_pytorch``, which this image does not ship; constructing it without
-    that package raises."""
+    """Out of the hot-path scope: the reference's learned U-Net++ processor (pipeline_torch.py:83-126)
+    is a CNN from ``segmentation_models_pytorch``, not an ISP kernel.  Import-safe stub with the reference's constructor
+    signature: constructing it raises."""
 
     def __init__(self, track_stages=False, normalize_mosaic=None, batch_norm_output=True):
         super().__init__()
-        try:
-            import segmentation_models_pytorch as smp
-        except ImportError as e:   # pragma: no cover - depends on the environment
-            raise ImportError("NNProcessing needs segmentation_models_pytorch (not part of the ISP hot path)") from e
-        self.stages = None
-        self.buffer = None
-        self.track_stages = track_stages
-        self.model = smp.UnetPlusPlus(encoder_name='resnet34', encoder_depth=3, decoder_channels=[256, 128, 64],
-                                      in_channels=3, classes=3)
-        self.batch_norm = None if not batch_norm_output else nn.BatchNorm2d(3, affine=False)
-        self.normalize_mosaic = normalize_mosaic
-
-    def forward(self, raw):
-        self.stages = {}
-        self.buffer = {}
-        rgb = raw2rgb(raw)
-        if self.normalize_mosaic:
-            rgb = self.normalize_mosaic(rgb)
-        self.stages['demosaic'] = rgb
-        rgb = self.model(rgb)
-        if self.batch_norm is not None:
-            rgb = self.batch_norm(rgb)
-        self.stages['rgb'] = rgb
-        if self.track_stages and raw.requires_grad:
-            for stage in self.stages.values():
-                stage.retain_grad()
-        self.buffer['processed_rgb'] = rgb
-        return rgb
+        raise NotImplementedError("NNProcessing (U-Net++ from segmentation_models_pytorch) is outside the ISP hot path "
+                                  "this package replaces; use the reference's class for processing_mode=neural_network")
 
 
 def append_additive_layer(processor):
