@@ -6,7 +6,6 @@
 #include "isp_fwd3.cuh"
 #include "isp_bwd4.cuh"
 #include "isp_bwd5.cuh"
-#include "isp_bwd6.cuh"
 
 namespace r2l {
 using FwdDefault = FwdCfg<32, 64, 256>;          // v1 (scalar) -- kept for the emulation cross-check only
@@ -22,7 +21,5 @@ constexpr int kBwd4CtasPerSm = 2;
 // v5: v4 with the running sums parked in tensor memory, 256 threads x 2 CTAs per SM at <= 128 registers
 template <bool GRAW, bool TAIL> using Bwd5 = Bwd5Cfg<32, 64, 256, GRAW, TAIL>;
 constexpr int kBwd5CtasPerSm = 2;
-// v6: warp-specialised dataflow pipeline, one 16-warp CTA per SM; <GRAW, TAIL, B4 / B5 / B6 / B7 warps>
-template <bool GRAW, bool TAIL> using Bwd6 = Bwd6Cfg<GRAW, TAIL, 4, 4, 2, 5>;
 constexpr int kMaxCtas = 2048;          // upper bound on persistent CTAs == rows of the statistics workspace
 }  // namespace r2l

@@ -414,22 +414,6 @@ bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_bytes, int 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool make_plane_tensor_map(CUtensorMap* map, const float* x, int B, int H, int W, int box_w, int box_h) {
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn) return false;
-    if (const char* off = getenv("R2L_ISP_NO_TMA")) {
-        if (off[0] == '1') return false;
-    }
-    if ((reinterpret_cast<uintptr_t>(x) & 15) || (W % 4) != 0) return false;
-    const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, 3u, (cuuint64_t)B};
-    const cuuint64_t gstride[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * 12};
-    const cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 3u, 2u};
-    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstride, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // the fused finish's ticket counter lives behind the per-CTA statistics rows of the workspace
 constexpr size_t kTicketOffset = (size_t)kMaxCtas * kStatPitch * sizeof(float);
 
@@ -468,11 +452,7 @@ static int launch_backward_any(const BwdArgs& a, int raw_dtype, float* grads, cu
             BwdArgs a4 = a;
             a4.grads = grads;
             a4.ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.partials) + kTicketOffset);
-            const char* gen = getenv("R2L_ISP_BWD_GEN");            // debugging knob: 5 = the tile-phased predecessor
-            if (!(gen && gen[0] == '5'))
-                rc = raw_dtype == R2L_F32 ? launch_backward6_f32(a4, st, &g) : launch_backward6_u16(a4, st, &g);
-            if (rc == kNotServed)
-                rc = raw_dtype == R2L_F32 ? launch_backward5_f32(a4, st, &g) : launch_backward5_u16(a4, st, &g);
+            rc = raw_dtype == R2L_F32 ? launch_backward5_f32(a4, st, &g) : launch_backward5_u16(a4, st, &g);
             if (rc == R2L_OK) return rc;
         }
         if (a.world > 1) return rc == kNotServed ? (int)R2L_ERR_BAD_ARGUMENT : rc;   // the exchange lives in that kernel only

@@ -38,9 +38,6 @@ static int persistent_grid(K kernel, int threads, size_t smem, int n_tiles, int*
 // false when the shape/pointer does not meet TMA's 16-byte rules (then a non-TMA kernel runs)
 bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_bytes, int B, int H, int W, int box_w, int box_h);
 
-// tensor map over a (B, 3, H, W) fp32 tensor: dims (W, H, 3, B), box (box_w, box_h, 3, 2), zero fill outside
-bool make_plane_tensor_map(CUtensorMap* map, const float* x, int B, int H, int W, int box_w, int box_h);
-
 // launchers, one translation unit each (compiled in parallel by _build.py)
 int launch_forward_f32(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used);
 int launch_forward_u16(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used);
@@ -50,9 +47,6 @@ int launch_backward3_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
 // fifth-generation backward (forward output + saved luma planes, running sums in tensor memory, fused finish)
 int launch_backward5_f32(const BwdArgs& a, cudaStream_t st, int* grid_used);
 int launch_backward5_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
-// sixth-generation backward (warp-specialised dataflow pipeline, TMA-fed; same inputs as the fifth)
-int launch_backward6_f32(const BwdArgs& a, cudaStream_t st, int* grid_used);
-int launch_backward6_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
 // generic scalar kernels: any shape, any alignment
 int launch_backward_generic(const BwdArgs& a, int raw_dtype, cudaStream_t st, int* grid_used);
 constexpr int kNotServed = 1;

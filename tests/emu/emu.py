@@ -15,7 +15,6 @@ DEPS = [SRC, os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_core.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_fwd3.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd4.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd5.cuh"),
-        os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_bwd6.cuh"),
         os.path.join(ROOT, "raw2logit_b200", "csrc", "isp_config.h"), os.path.join(ROOT, "include", "r2l_isp.h")]
 
 PARAM_FIELDS = ["black_level", "white_balance", "colour_correction", "gamma_correct", "debayer.weight",
@@ -36,7 +35,7 @@ class Tail(ctypes.Structure):
 def build():
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in DEPS):
         return LIB
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-o", LIB, SRC])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC])
     return LIB
 
 

@@ -6,9 +6,6 @@
 #define R2L_HOST_EMU 1
 #include <vector>
 #include <cstring>
-#include <cmath>
-#include <thread>
-#include <atomic>
 #include "../../include/r2l_isp.h"
 #include "../../raw2logit_b200/csrc/isp_config.h"
 
@@ -48,64 +45,13 @@ static void run_forward(const FwdArgs& a, int n_cta) {
     for (int cta = 0; cta < n_cta; ++cta) fwd2_cta<Cfg, RawT, STATS>(cta, n_cta, a, grid, base);
 }
 
-// sixth generation: every warp of the CTA is a host thread (blocking waits on the progress words, like on the GPU);
-// the lanes of a warp run one after another.  Returns false when a wait never ended (a dependency bug).
-template <class C6, typename RawT>
-static bool run_backward6(const BwdArgs& a, int n_cta) {
-    bool ok = true;
-    for (int cta = 0; cta < n_cta; ++cta) {
-        std::vector<float> tab(C6::kTableFloats + 4, 0.f);
-        float* tbase = tab.data();
-        while (reinterpret_cast<uintptr_t>(tbase) % 16) ++tbase;
-        Tables2* T2 = reinterpret_cast<Tables2*>(tbase);
-        R2L_BUILD_TABLES(64, a.P, &T2->base)
-        std::vector<float> rings((size_t)C6::kRingSites * 2 + 4, 0.f);
-        float* rbase = rings.data();
-        while (reinterpret_cast<uintptr_t>(rbase) % 16) ++rbase;
-        std::vector<float> stage((size_t)kB6NS * kB6SlotFloats + 4, 0.f);
-        float* sbase = stage.data();
-        while (reinterpret_cast<uintptr_t>(sbase) % 16) ++sbase;
-        std::vector<float> red((size_t)C6::NW * 128, 0.f), park((size_t)C6::N7 * 32 * 3 * kB6K, 0.f);
-        Sync6 sy;
-        for (int i = 0; i < 8; ++i) {
-            sy.done4[i] = 0; sy.done5[i] = 0; sy.done6[i] = 0; sy.low5[i] = 0; sy.low6[i] = 0; sy.low7a[i] = 0; sy.low7b[i] = 0; sy.pad[i] = 0;
-        }
-        sync6_t full_seq[kB6NS], empty_seq[kB6NS];
-        for (int i = 0; i < kB6NS; ++i) { full_seq[i] = 0; empty_seq[i] = 0; }
-        Ctx6<C6> cx;
-        cx.a = &a; cx.T2 = T2; cx.sy = &sy;
-        cx.gY2 = reinterpret_cast<f2*>(rbase);
-        cx.gY1 = cx.gY2 + kB6R4 * kB6P; cx.gY0 = cx.gY1 + kB6R5 * kB6P; cx.gU = cx.gY0 + kB6R6 * kB6P; cx.gV = cx.gU + kB6RUV * kB6P;
-        cx.stage = sbase; cx.red = red.data(); cx.full_seq = full_seq; cx.empty_seq = empty_seq; cx.park = park.data();
-        cx.cta = cta; cx.n_cta = n_cta;
-        std::atomic<int> failed(0);
-        std::vector<std::thread> th;
-        auto guard = [&](auto fn) { th.emplace_back([&failed, fn]() { try { fn(); } catch (Emu6Abort&) { failed = 1; } }); };
-        for (int w = 0; w < C6::N4; ++w) guard([&cx, w]() { b6_role_b4<C6, RawT>(cx, w); });
-        for (int w = 0; w < C6::N5; ++w) guard([&cx, w]() { b6_role_b5<C6, RawT>(cx, w); });
-        for (int w = 0; w < C6::N6; ++w) guard([&cx, w]() { b6_role_b6<C6, RawT>(cx, w); });
-        for (int w = 0; w < C6::N7; ++w) guard([&cx, w]() { b6_role_b7<C6, RawT>(cx, w); });
-        guard([&cx]() { b6_role_tma<C6>(cx); });
-        for (auto& t : th) t.join();
-        if (failed) ok = false;
-        float* part = a.partials + (size_t)cta * kStatPitch;
-        for (int s = 0; s < kNumStats; ++s) part[s] = b6_stat<C6>(red.data(), s);
-    }
-    return ok;
-}
-
 template <class Cfg, typename RawT>
 static void run_backward(const BwdArgs& a, int n_cta, float* grads, int version) {
-    if (version == 6 && a.out && a.luma && bwd6_shape_ok(a.H, a.W)) {
-        bool ok;
-        if (a.gtail) ok = run_backward6<Bwd6<Cfg::GRAW, true>, RawT>(a, n_cta);
-        else ok = run_backward6<Bwd6<Cfg::GRAW, false>, RawT>(a, n_cta);
-        if (!ok) { for (int e = 0; e < R2L_NUM_PARAM_GRADS; ++e) grads[e] = NAN; return; }
-    } else if (version == 1) {
+    if (version == 1) {
         const TileGrid grid = make_grid(a.B, a.H, a.W, Cfg::TH, Cfg::TW);
         std::vector<float> smem(Cfg::kSmemFloats);
         for (int cta = 0; cta < n_cta; ++cta) bwd_cta<Cfg, RawT>(cta, n_cta, a, grid, smem.data());
-    } else if ((version == 5 || version == 6) && a.out && a.luma && bwd5_shape_ok(a.H, a.W)) {     // same dispatch rule as the CUDA launcher
+    } else if (version == 5 && a.out && a.luma && bwd5_shape_ok(a.H, a.W)) {     // same dispatch rule as the CUDA launcher
         auto go5 = [&](auto cfg) {
             using C5 = decltype(cfg);
             const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, C5::TH, C5::TW);
@@ -127,7 +73,7 @@ static void run_backward(const BwdArgs& a, int n_cta, float* grads, int version)
         };
         if (a.gtail) go4(Bwd4<Cfg::GRAW, true>());
         else go4(Bwd4<Cfg::GRAW, false>());
-    } else if (version == 3 || version == 4 || version == 5 || version == 6) {
+    } else if (version == 3 || version == 4 || version == 5) {
         if (!bwd3_shape_ok(a.H, a.W, Cfg::TH, Cfg::TW)) {           // same dispatch rule as the CUDA launcher
             run_backward<Cfg, RawT>(a, n_cta, grads, 1);
             return;
