@@ -41,6 +41,42 @@ def is_stale():
     return any(os.path.getmtime(p) > built for p in sources() + headers())
 
 
+# ---- torch operator shim (TORCH_LIBRARY + C++ autograd node): raw2logit_b200/libr2l_torch.so -------------------------
+TORCH_SRC = os.path.join(HERE, "csrc_torch", "r2l_torch.cpp")
+TORCH_LIB_PATH = os.path.join(HERE, "libr2l_torch.so")
+
+
+def torch_shim_is_stale():
+    if not os.path.exists(TORCH_LIB_PATH):
+        return True
+    built = os.path.getmtime(TORCH_LIB_PATH)
+    deps = [TORCH_SRC, os.path.join(ROOT, "include", "r2l_isp.h")]
+    return any(os.path.getmtime(p) > built for p in deps)
+
+
+def build_torch_shim(force=False):
+    """g++ on csrc_torch/r2l_torch.cpp against the installed torch headers; links libr2l_isp.so by $ORIGIN rpath."""
+    if not force and not torch_shim_is_stale():
+        return TORCH_LIB_PATH
+    import torch
+    from torch.utils import cpp_extension as ce
+    cuda_home = os.path.dirname(os.path.dirname(nvcc_path()))
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", TORCH_LIB_PATH + ".tmp", TORCH_SRC,
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(cuda_home, "include")]
+    for inc in ce.include_paths():
+        cmd += ["-isystem", inc]
+    for lib in ce.library_paths():
+        cmd += ["-L", lib, f"-Wl,-rpath,{lib}"]
+    cmd += ["-L", HERE, "-l:libr2l_isp.so", "-Wl,-rpath,$ORIGIN", "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda",
+            "-ltorch_cuda"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed on the torch shim:\n" + res.stdout + res.stderr)
+    os.replace(TORCH_LIB_PATH + ".tmp", TORCH_LIB_PATH)
+    return TORCH_LIB_PATH
+
+
 def _obj_path(src):
     return os.path.join(OBJ, os.path.splitext(os.path.basename(src))[0] + ".o")
 

@@ -49,12 +49,12 @@ def raw2rgb(raw, black_level=None, reduce_size=True, out_channels=3, raw_denomin
     """
     assert out_channels in [3, 4]
     _require_cuda(raw)
-    if black_level is None:
-        if raw.requires_grad:
-            return ops.Mosaic.apply(raw, reduce_size, out_channels, float(raw_denominator))
-        return torch.ops.raw2logit_isp.mosaic(raw, None, bool(reduce_size), int(out_channels), float(raw_denominator))
-    bl = torch.as_tensor(black_level, dtype=torch.float32, device=raw.device).detach().reshape(4)
-    return torch.ops.raw2logit_isp.mosaic(raw, bl, bool(reduce_size), int(out_channels), float(raw_denominator))
+    bl = None
+    if black_level is not None:
+        bl = black_level if isinstance(black_level, torch.Tensor) else torch.as_tensor(black_level, dtype=torch.float32)
+        bl = bl.to(device=raw.device, dtype=torch.float32).reshape(4)
+    # differentiable in raw and black_level, like the reference's indexing arithmetic (:256-259, :273-277)
+    return ops.mosaic(raw, bl, reduce_size, out_channels, raw_denominator)
 
 
 class RawToRGB(nn.Module):
