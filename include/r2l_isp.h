@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define R2L_ABI_VERSION 4
+#define R2L_ABI_VERSION 5
 
 enum {
     R2L_OK = 0,
@@ -149,11 +149,15 @@ int r2l_isp_backward(const void* raw, int raw_dtype, float raw_denominator, int 
  *   peers     DEVICE array of `world` pointers; peers[r] = rank r's exchange buffer as mapped into THIS process
  *             (CUDA IPC / symmetric memory, e.g. torch.distributed._symmetric_memory: buffer_ptrs_dev), each
  *             r2l_isp_exchange_bytes(world) bytes, zero-filled once before the first call
- *   epoch     1, 2, 3, ... -- the same value on every rank, incremented on every call that uses the buffer
+ *   epoch     1, 2, 3, ... -- the same value on every rank, incremented on every call that uses the buffer; or
+ *             R2L_EPOCH_DEVICE: the kernel keeps the count itself, in a word at the end of this rank's exchange buffer
+ *             (every rank makes the same calls, so the counts agree) -- the launch then carries no per-call value and
+ *             can be captured in a CUDA graph and replayed.  One buffer must be used in one of the two ways only.
  *   scale     factor applied to the sum (1/world for an average, 1 for a sum)
  * Needs the path that finishes the gradients in the launch (out and saved_luma given, shape served by the vectorised
  * kernel); otherwise R2L_ERR_BAD_ARGUMENT and nothing is launched (use r2l_isp_backward + a collective).  Every rank
  * must make the call, or the others wait for ever, as with any collective. */
+#define R2L_EPOCH_DEVICE 0xFFFFFFFFu
 typedef struct {
     int world, rank;
     float* const* peers;

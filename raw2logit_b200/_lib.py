@@ -18,7 +18,8 @@ GRAD_LAYOUT = {
     "gauss_weight": (107, 25, (1, 1, 5, 5)),
 }
 F32, U16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
+EPOCH_DEVICE = 0xFFFFFFFF   # R2L_EPOCH_DEVICE: the kernel keeps the exchange epoch itself (graph-capturable)
 
 EXPORTS = ("r2l_isp_abi_version", "r2l_isp_error_string", "r2l_isp_last_cuda_error", "r2l_isp_forward",
            "r2l_isp_workspace_bytes", "r2l_isp_forward_bn_train", "r2l_isp_bn_backward_prepare", "r2l_isp_backward",

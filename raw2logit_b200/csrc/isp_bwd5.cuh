@@ -106,7 +106,22 @@ template <int NT> __device__ __forceinline__ void peer_allreduce(const BwdArgs& 
     static_assert(kSlotPitch >= R2L_NUM_PARAM_GRADS, "one tagged word per gradient");
     static_assert(NT >= R2L_NUM_PARAM_GRADS, "thread e owns gradient e from its local read to its final write");
     const int world = a.world, e = threadIdx.x;
-    const size_t slot0 = (size_t)(a.epoch & 1u) * world * (2 * kSlotPitch);      // floats; a slot = kSlotPitch words of 8 bytes
+    unsigned epoch = a.epoch;
+    if (epoch == R2L_EPOCH_DEVICE) {
+        // the count lives in the word behind this rank's slots (local memory; only this CTA of this launch touches it,
+        // and launches on one stream run in order): nothing per call comes from the host, so a captured launch replays
+        __shared__ unsigned s_epoch;
+        if (e == 0) {
+            unsigned* c = reinterpret_cast<unsigned*>(a.peers[a.rank] + (size_t)2 * world * (2 * kSlotPitch));
+            unsigned v = *c + 1u;
+            if (v == R2L_EPOCH_DEVICE || v == 0u) v = 1u;
+            *c = v;
+            s_epoch = v;
+        }
+        __syncthreads();
+        epoch = s_epoch;
+    }
+    const size_t slot0 = (size_t)(epoch & 1u) * world * (2 * kSlotPitch);        // floats; a slot = kSlotPitch words of 8 bytes
     __syncthreads();                                                     // a.grads of this launch are written
     if (e < R2L_NUM_PARAM_GRADS) {
         // Thread e is the only one that touches a.grads[e] from here on: it reads the local value once, pushes it to
@@ -115,12 +130,12 @@ template <int NT> __device__ __forceinline__ void peer_allreduce(const BwdArgs& 
         // the reduced sum -- ADVICE round 1.)
         const float local = a.grads[e];
         for (int p = 0; p < world; ++p)
-            st_tagged_sys(a.peers[p] + slot0 + (size_t)a.rank * (2 * kSlotPitch) + 2 * e, local, a.epoch);
+            st_tagged_sys(a.peers[p] + slot0 + (size_t)a.rank * (2 * kSlotPitch) + 2 * e, local, epoch);
         const float* mine = a.peers[a.rank] + slot0;
         const unsigned long long deadline = global_timer_ns() + kExchangeTimeoutNs;
         bool ok = true;
         float sum = 0.f;
-        for (int r = 0; r < world; ++r) sum += ld_tagged_sys(mine + (size_t)r * (2 * kSlotPitch) + 2 * e, a.epoch, deadline, &ok);
+        for (int r = 0; r < world; ++r) sum += ld_tagged_sys(mine + (size_t)r * (2 * kSlotPitch) + 2 * e, epoch, deadline, &ok);
         a.grads[e] = ok ? sum * a.dp_scale : __int_as_float(0x7fc00000);
     }
 }

@@ -574,7 +574,7 @@ int r2l_isp_bn_backward_prepare(const float* grad_out, const float* out, const f
 
 size_t r2l_isp_exchange_bytes(int world) {
     if (world < 1 || world > kMaxWorld) return 0;
-    return (size_t)2 * world * kSlotPitch * 8;
+    return (size_t)2 * world * kSlotPitch * 8 + 16;            // + the device-side epoch counter (R2L_EPOCH_DEVICE)
 }
 
 static int backward_impl(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,

@@ -104,7 +104,6 @@ struct Exchange {
     bool on = false;
     int world = 1, rank = 0;
     int64_t peers = 0;
-    unsigned epoch = 0;
     float scale = 1.f;
 };
 std::mutex g_xch_mutex;
@@ -225,14 +224,15 @@ std::tuple<Tensor, Tensor> backward_cuda(const Tensor& raw_, const Tensor& bl, c
     Exchange x;
     {
         std::lock_guard<std::mutex> lock(g_xch_mutex);
-        if (g_xch.on) { ++g_xch.epoch; x = g_xch; }
+        x = g_xch;
     }
     int rc;
     if (x.on) {
         // data-parallel: the 132 gradients leave the kernel already reduced over the ranks (parallel.PeerExchange)
         TORCH_CHECK(y.defined() && lum.defined(), "the fused gradient exchange needs the saved output and luma planes "
                     "(unset R2L_ISP_RECOMPUTE / R2L_ISP_NO_LUMA, shapes with W % 4 == 0)");
-        r2l_isp_allreduce d{x.world, x.rank, reinterpret_cast<float* const*>(x.peers), x.epoch, x.scale};
+        // the kernel keeps the epoch in the exchange buffer: nothing per call comes from the host (graph replays)
+        r2l_isp_allreduce d{x.world, x.rank, reinterpret_cast<float* const*>(x.peers), R2L_EPOCH_DEVICE, x.scale};
         rc = r2l_isp_backward_dp(raw.data_ptr(), code, (float)raw_denominator, b, h, w, &pk.p, g.data_ptr<float>(), fp(gs),
                                  fp(add), fp(y), fp(lum), need_raw_grad ? graw.data_ptr<float>() : nullptr,
                                  gpar.data_ptr<float>(), wsb.data_ptr(), nbytes, &d, cur_stream(raw));
@@ -292,14 +292,9 @@ Tensor batch_sum_cuda(const Tensor& x, const optional<Tensor>& scale) {
     return out;
 }
 
-void set_exchange(int64_t world, int64_t rank, int64_t peers, int64_t epoch, double scale, bool on) {
+void set_exchange(int64_t world, int64_t rank, int64_t peers, double scale, bool on) {
     std::lock_guard<std::mutex> lock(g_xch_mutex);
-    g_xch.on = on; g_xch.world = (int)world; g_xch.rank = (int)rank; g_xch.peers = peers;
-    g_xch.epoch = (unsigned)epoch; g_xch.scale = (float)scale;
-}
-int64_t exchange_epoch() {
-    std::lock_guard<std::mutex> lock(g_xch_mutex);
-    return (int64_t)g_xch.epoch;
+    g_xch.on = on; g_xch.world = (int)world; g_xch.rank = (int)rank; g_xch.peers = peers; g_xch.scale = (float)scale;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -525,8 +520,7 @@ TORCH_LIBRARY(raw2logit_isp, m) {
           "Tensor(b!)? running_var, float momentum, float eps, float raw_denominator) -> Tensor");
     m.def("mosaic_ad(Tensor raw, Tensor? black_level, bool reduce_size, int out_channels, float raw_denominator) -> Tensor");
     // process-wide state of the fused data-parallel exchange (parallel.enable_fused_gradient_exchange)
-    m.def("set_exchange(int world, int rank, int peers, int epoch, float scale, bool on) -> ()", &set_exchange);
-    m.def("exchange_epoch() -> int", &exchange_epoch);
+    m.def("set_exchange(int world, int rank, int peers, float scale, bool on) -> ()", &set_exchange);
 }
 
 TORCH_LIBRARY_IMPL(raw2logit_isp, CUDA, m) {

@@ -11,7 +11,7 @@ dispatcher call, one forward kernel launch and one backward launch.
 
 Operators (schemas in r2l_torch.cpp): ``forward``, ``forward_bn_train``, ``bn_backward_prepare``, ``backward``,
 ``mosaic``, ``mosaic_backward``, ``batch_sum`` (plain, one C-ABI call each); ``fused`` and ``mosaic_ad`` (differentiable:
-C++ autograd nodes); ``set_exchange`` / ``exchange_epoch`` (state of the fused data-parallel gradient exchange).
+C++ autograd nodes); ``set_exchange`` (state of the fused data-parallel gradient exchange).
 """
 import os
 
@@ -43,17 +43,14 @@ _exchange_average = True
 def set_gradient_exchange(exchange, average=True):
     """``exchange``: a ``parallel.PeerExchange`` (every later fused backward on this process sums / averages its 132
     parameter gradients over the ranks inside the kernel) or None (local gradients).  Every rank must run the same
-    sequence of backward calls while it is set.  The epoch counter lives in the operator library while the exchange
-    is on and is handed back to the ``PeerExchange`` when it is switched off."""
+    sequence of backward calls while it is set.  The kernel keeps the exchange epoch in the buffer itself
+    (``R2L_EPOCH_DEVICE``), so the step may be captured in a CUDA graph and replayed."""
     global _exchange, _exchange_average
-    if _exchange is not None and hasattr(_exchange, "epoch"):
-        _exchange.epoch = int(_ops.exchange_epoch())
     _exchange, _exchange_average = exchange, bool(average)
     if exchange is None or not hasattr(exchange, "peers"):
-        _ops.set_exchange(1, 0, 0, 0, 1.0, False)
+        _ops.set_exchange(1, 0, 0, 1.0, False)
     else:
-        _ops.set_exchange(exchange.world, exchange.rank, exchange.peers, exchange.epoch,
-                          1.0 / exchange.world if average else 1.0, True)
+        _ops.set_exchange(exchange.world, exchange.rank, exchange.peers, 1.0 / exchange.world if average else 1.0, True)
 
 
 def fused_isp(raw, black_level, white_balance, colour_correction, gamma_correct, debayer_weight, sharpen_weight,

@@ -89,13 +89,15 @@ class PeerExchange:
         torch.cuda.synchronize(device)
         dist.barrier(group)                                          # every rank's flags are zero before anyone writes
         self.peers = int(self.handle.buffer_ptrs_dev)                # device array of `world` buffer pointers
-        self.epoch = 0
+        self.calls = 0
 
     def next(self, average=True):
-        """Descriptor for the next ``r2l_isp_backward_dp`` call (``_lib.IspAllreduce``)."""
+        """Descriptor for the next ``r2l_isp_backward_dp`` call (``_lib.IspAllreduce``).  The epoch is kept by the
+        kernel itself in the exchange buffer (``R2L_EPOCH_DEVICE``), so a captured launch can be replayed."""
         from . import _lib
-        self.epoch += 1
-        return _lib.IspAllreduce(self.world, self.rank, self.peers, self.epoch, 1.0 / self.world if average else 1.0)
+        self.calls += 1
+        return _lib.IspAllreduce(self.world, self.rank, self.peers, _lib.EPOCH_DEVICE,
+                                 1.0 / self.world if average else 1.0)
 
 
 def enable_fused_gradient_exchange(group=None, average=True):

@@ -16,7 +16,7 @@ def test_exchange_abi_without_gpu():
     lib = _lib.load()
     assert lib.r2l_isp_exchange_bytes(0) == 0 and lib.r2l_isp_exchange_bytes(17) == 0
     for world in (1, 2, 4, 8, 16):
-        assert lib.r2l_isp_exchange_bytes(world) == 2 * world * 136 * 8
+        assert lib.r2l_isp_exchange_bytes(world) == 2 * world * 136 * 8 + 16      # + the device-side epoch word
     null = ctypes.c_void_p(None)
     args = [null, _lib.F32, 65535.0, 2, 8, 8, None, null, null, null, null, null, null, null, null, 0]
     assert lib.r2l_isp_backward_dp(*args, None, null) == -3                       # R2L_ERR_NULL_POINTER: no descriptor
