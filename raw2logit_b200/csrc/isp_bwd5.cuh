@@ -70,6 +70,29 @@ struct Bwd5Acc { float sums[kBwd5AccFloats]; };
 #endif
 
 #ifndef R2L_HOST_EMU
+// ---- ticket of the fused finish: one 64-bit word {count (low), generation (high)} in the workspace.  A launch owns the
+// word once its generation tag is in it: whatever the word held before (an uninitialised workspace, the previous
+// launch's final count) is replaced by {gen, 0} by the first CTA to arrive -- no memset in front of the kernel (which
+// would also sit between this kernel and the one before it on the stream), no zero-fill contract.  The last CTA clears
+// the word, so a captured launch (same tag at every replay) starts clean as well.
+// Returns this CTA's ticket 0 .. n_cta-1.  The count itself is ONE atomic add per CTA (a compare-and-swap loop here made
+// the 160 CTAs that finish their third tile together retry against each other: +86 us at 64 x 256 x 256,
+// profiles/r02_summary.md); only a CTA that finds a foreign tag makes one compare-and-swap attempt to install this
+// launch's tag first -- if that fails, another CTA of this launch has installed it.
+__device__ __forceinline__ unsigned take_ticket(unsigned* ticket, unsigned gen) {
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(ticket);
+    volatile unsigned long long* vw = reinterpret_cast<volatile unsigned long long*>(w);
+    unsigned long long cur = *vw;
+    if ((unsigned)(cur >> 32) != gen) {
+        atomicCAS(w, cur, (unsigned long long)gen << 32);
+        do { cur = *vw; } while ((unsigned)(cur >> 32) != gen);
+    }
+    return (unsigned)atomicAdd(w, 1ull);
+}
+__device__ __forceinline__ void clear_ticket(unsigned* ticket) {
+    *reinterpret_cast<volatile unsigned long long*>(ticket) = 0ull;
+}
+
 // ---- one-shot all-reduce of the 132 gradients over NVLink peer memory, run by the CTA that finished them ------------
 // (r2l_isp_backward_dp, include/r2l_isp.h).  Every gradient travels as one 8-byte word {value, epoch} written by ONE
 // 64-bit store (single-copy atomic), so the epoch tag tells the reader that the value next to it is this step's -- no
@@ -104,14 +127,13 @@ __device__ __forceinline__ float ld_tagged_sys(const float* p, unsigned tag, uns
 constexpr unsigned long long kExchangeTimeoutNs = 5000000000ull;        // 5 s
 template <int NT> __device__ __forceinline__ void peer_allreduce(const BwdArgs& a) {
     static_assert(kSlotPitch >= R2L_NUM_PARAM_GRADS, "one tagged word per gradient");
-    static_assert(NT >= R2L_NUM_PARAM_GRADS, "thread e owns gradient e from its local read to its final write");
-    const int world = a.world, e = threadIdx.x;
+    const int world = a.world, e0 = threadIdx.x;
     unsigned epoch = a.epoch;
     if (epoch == R2L_EPOCH_DEVICE) {
         // the count lives in the word behind this rank's slots (local memory; only this CTA of this launch touches it,
         // and launches on one stream run in order): nothing per call comes from the host, so a captured launch replays
         __shared__ unsigned s_epoch;
-        if (e == 0) {
+        if (e0 == 0) {
             unsigned* c = reinterpret_cast<unsigned*>(a.peers[a.rank] + (size_t)2 * world * (2 * kSlotPitch));
             unsigned v = *c + 1u;
             if (v == R2L_EPOCH_DEVICE || v == 0u) v = 1u;
@@ -123,8 +145,8 @@ template <int NT> __device__ __forceinline__ void peer_allreduce(const BwdArgs& 
     }
     const size_t slot0 = (size_t)(epoch & 1u) * world * (2 * kSlotPitch);        // floats; a slot = kSlotPitch words of 8 bytes
     __syncthreads();                                                     // a.grads of this launch are written
-    if (e < R2L_NUM_PARAM_GRADS) {
-        // Thread e is the only one that touches a.grads[e] from here on: it reads the local value once, pushes it to
+    for (int e = e0; e < R2L_NUM_PARAM_GRADS; e += NT) {            // (one pass when the CTA has >= 132 threads)
+        // Thread e % NT is the only one that touches a.grads[e] from here on: it reads the local value once, pushes it to
         // every rank, then pulls every rank's word e and writes the sum back.  (A version whose push loop ran over
         // (rank, gradient) pairs let another thread push a.grads[e] after thread e had already overwritten it with
         // the reduced sum -- ADVICE round 1.)
@@ -155,6 +177,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
     std::vector<Bwd5Acc> accs(NT);
     std::memset(accs.data(), 0, sizeof(Bwd5Acc) * NT);
 #else
+    pdl_launch_dependents();                                      // the next kernel's CTAs may take the slots we free
     // TMEM columns for the running sums: warp 0 allocates, everybody zeroes its own cells
     __shared__ uint32_t tmem_slot;
     if (threadIdx.x < 32) tmem::alloc<Cfg::kTmemCols>(&tmem_slot);
@@ -182,6 +205,13 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
     R2L_BUILD_TABLES(NT, a.P, T)
     { R2L_FOR_THREADS(NT) { build_tables2_extra(tid, NT, T2); } }
     R2L_SYNC();
+#ifndef R2L_HOST_EMU
+    // Under a dependent launch (R2L_ISP_BWD_PDL=1; off by default -- it measured slower, profiles/r02_summary.md) everything
+    // up to here may run while the kernel before this one drains: it touched only the parameters (never written by this
+    // library's kernels), shared and tensor memory.  The forward output, the luma planes and grad_out are read -- and the
+    // workspace, grad_raw, the gradients written -- after the wait.  A no-op for a plain launch.
+    pdl_wait();
+#endif
     for (int tile = cta; tile < grid.n; tile += n_cta) {
         int b0, b1, ty0, tx0;
         decode_pair_tile(grid, tile, TH, TW, a.B, b0, b1, ty0, tx0);
@@ -801,11 +831,12 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         __shared__ unsigned last_flag;
         __threadfence();                                             // this CTA's partial sums are visible device-wide ...
         __syncthreads();
-        if (threadIdx.x == 0) last_flag = atomicAdd(a.ticket, 1u) == (unsigned)n_cta - 1u;   // ... before its ticket is
+        if (threadIdx.x == 0) last_flag = take_ticket(a.ticket, a.ticket_gen) == (unsigned)n_cta - 1u;   // ... before its ticket is
         __syncthreads();
         if (last_flag) {
             __threadfence();
             static_assert((size_t)(NT / 32 + 1) * kStatPitch * 8 + 130 * 8 <= (size_t)Cfg::kSites * 8, "finish scratch fits the planes");
+            if (threadIdx.x == 0) clear_ticket(a.ticket);
             fused_finish<NT>(T, a.partials, n_cta, a.grads, reinterpret_cast<double*>(PU));
             if (a.world > 1) peer_allreduce<NT>(a);
         }

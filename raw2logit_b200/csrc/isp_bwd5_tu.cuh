@@ -20,13 +20,10 @@ static int launch_backward5_t(const BwdArgs& a, cudaStream_t st, int* grid_used)
     if (g > grid.n) g = grid.n;
     if (g > kMaxCtas) g = kMaxCtas;
     if (rc != R2L_OK) return rc;
-    if (a.ticket) {
-        cudaError_t e0 = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned), st);
-        if (e0 != cudaSuccess) return cuda_fail(e0);
-    }
-    isp_backward5_kernel<Cfg, RawT, CPS><<<g, Cfg::NT, Cfg::kSmemBytes, st>>>(a, grid);
+    BwdArgs a2 = a;
+    a2.ticket_gen = next_ticket_generation();                   // no memset in front of the kernel (take_ticket, isp_bwd5.cuh)
+    cudaError_t e = launch_pdl(pdl_enabled_backward(), isp_backward5_kernel<Cfg, RawT, CPS>, g, Cfg::NT, Cfg::kSmemBytes, st, a2, grid);
     if (grid_used) *grid_used = g;
-    cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);
 }
 

@@ -19,7 +19,12 @@ template <bool GRAW, bool TAIL, bool OUT = false> using Bwd3 = Bwd3Cfg<32, 64, 2
 template <bool GRAW, bool TAIL> using Bwd4 = Bwd4Cfg<32, 64, 128, GRAW, TAIL>;
 constexpr int kBwd4CtasPerSm = 2;
 // v5: v4 with the running sums parked in tensor memory, 256 threads x 2 CTAs per SM at <= 128 registers
-template <bool GRAW, bool TAIL> using Bwd5 = Bwd5Cfg<32, 64, 256, GRAW, TAIL>;
-constexpr int kBwd5CtasPerSm = 2;
+#ifndef R2L_B5_TH
+#define R2L_B5_TH 32
+#define R2L_B5_NT 256
+#define R2L_B5_CPS 2
+#endif
+template <bool GRAW, bool TAIL> using Bwd5 = Bwd5Cfg<R2L_B5_TH, 64, R2L_B5_NT, GRAW, TAIL>;
+constexpr int kBwd5CtasPerSm = R2L_B5_CPS;
 constexpr int kMaxCtas = 2048;          // upper bound on persistent CTAs == rows of the statistics workspace
 }  // namespace r2l

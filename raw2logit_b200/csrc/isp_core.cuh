@@ -469,7 +469,8 @@ struct BwdArgs {
                            // colour-tail recompute (the generic kernel ignores it)
     const float* luma = nullptr;   // null, or the Y0 / Y1 planes the forward saved (FwdArgs::luma): with `out`, the
                                    // fourth-generation backward recomputes nothing
-    unsigned* ticket = nullptr;    // device counter (zero on entry) for the fused finish: the last CTA to publish its
+    unsigned ticket_gen = 0;       // launch tag of the ticket word (never 0): {gen, count} -- see take_ticket()
+    unsigned* ticket = nullptr;    // 8-byte aligned device word {count, gen} for the fused finish: the last CTA to publish its
                                    // partial sums turns them into the 132 gradients (null: separate finish kernel)
     float* grads = nullptr;        // destination of the fused finish
     // data-parallel exchange fused into the finish (r2l_isp_backward_dp): peers[r] = rank r's exchange buffer

@@ -30,6 +30,22 @@ R2L_HD f2 fma2s(f2 a, float w, f2 c) { return __ffma2_rn(a, make_float2(w, w), c
 R2L_HD f2 mul2s(f2 a, float w) { return __fmul2_rn(a, make_float2(w, w)); }
 #endif
 
+#ifndef R2L_HOST_EMU
+// ---- programmatic dependent launch (PDL): the launcher sets cudaLaunchAttributeProgrammaticStreamSerialization, so this
+// kernel's CTAs may become resident while the kernel before it on the stream is still draining.  launch_dependents():
+// "the next kernel may start launching"; grid_dependency_wait(): blocks until the kernel(s) before this one have
+// completed and their memory is visible -- everything this kernel reads that a predecessor may have written, and
+// everything it writes, comes after it.  Both are no-ops when the launch carries no such attribute.
+#ifdef R2L_NO_PDL_ASM
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void pdl_wait() {}
+#else
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
+#endif
+
 // two adjacent float2 sites with one 16-byte access (p must be 16-byte aligned: even site index)
 R2L_HD void ld2(const f2* p, f2& a, f2& b) {
     const f4 v = *reinterpret_cast<const f4*>(p);

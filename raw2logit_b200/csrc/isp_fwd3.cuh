@@ -60,6 +60,8 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
     const int H = a.H, W = a.W;
     const size_t plane = (size_t)H * W;
 #ifndef R2L_HOST_EMU
+    pdl_launch_dependents();                     // the next kernel's CTAs may take the slots this grid frees
+    bool pdl_pending = true;                     // until the first tile reaches its first global store
     // the first tile's raw window is requested before anything else so the copy overlaps the CTA prologue
     RawT* stage = reinterpret_cast<RawT*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset + Cfg::kStageBytes);
@@ -102,6 +104,10 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
         } }
         R2L_SYNC();
 #ifndef R2L_HOST_EMU
+        // Dependent launch: the prologue, the first raw window (raw is never written by this library's kernels) and its
+        // de-interleave may run while the kernel before this one drains; everything this kernel WRITES (luma planes in
+        // F2, the output in F4, the channel sums) may still be read by that kernel, so the first store waits for it.
+        if (pdl_pending) { pdl_wait(); pdl_pending = false; }
         if (TMA && threadIdx.x == 0) {
             const int next = tile + n_cta;
             if (next < grid.n) {

@@ -52,9 +52,8 @@ static int launch_forward3_t(const FwdArgs& a, cudaStream_t st, int* grid_used) 
     int g = 0;
     int rc = persistent_grid(isp_forward3_kernel<Cfg, RawT, STATS, TAIL>, Cfg::NT, Cfg::kSmemBytesTma, grid.n, &g);
     if (rc != R2L_OK) return rc;
-    isp_forward3_kernel<Cfg, RawT, STATS, TAIL><<<g, Cfg::NT, Cfg::kSmemBytesTma, st>>>(a, grid, tmap);
+    cudaError_t e = launch_pdl(pdl_enabled(), isp_forward3_kernel<Cfg, RawT, STATS, TAIL>, g, Cfg::NT, Cfg::kSmemBytesTma, st, a, grid, tmap);
     if (grid_used) *grid_used = g;
-    cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);
 }
 

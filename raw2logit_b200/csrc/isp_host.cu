@@ -5,6 +5,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC  (see _build.py)
 // No torch headers, no host-side state: every call validates its arguments, enqueues kernels on the caller's
 // stream and returns.
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -426,6 +427,23 @@ static bool luma_path_ok(const void* raw, int raw_dtype, int H, int W, const flo
     const int eb = raw_dtype == R2L_F32 ? 4 : 2;
     return fwd3_shape_ok(H, W) && aligned(out, 16) && aligned(additive, 16) && aligned(raw, 16) &&
            ((size_t)W * eb) % 16 == 0;
+}
+
+unsigned next_ticket_generation() {
+    static std::atomic<unsigned> gen{0};
+    unsigned g = gen.fetch_add(1u) + 1u;
+    if (g == 0u) g = gen.fetch_add(1u) + 1u;
+    return g;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("R2L_ISP_NO_PDL"); return !(v && v[0] == '1'); }();
+    return on;
+}
+
+bool pdl_enabled_backward() {
+    static const bool on = [] { const char* v = getenv("R2L_ISP_BWD_PDL"); return v && v[0] == '1'; }();
+    return on && pdl_enabled();
 }
 
 // statistics of the backward CTAs -> 132 gradients

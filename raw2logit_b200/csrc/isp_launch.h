@@ -34,6 +34,34 @@ static int persistent_grid(K kernel, int threads, size_t smem, int n_tiles, int*
     return R2L_OK;
 }
 
+// launch tag of the fused finish's ticket word: 1, 2, 3, ... (never 0), process-wide
+unsigned next_ticket_generation();
+
+// <<<grid, threads, smem, st>>> with programmatic stream serialization allowed: the kernel may become resident while the
+// kernel before it on the stream drains; it orders itself behind that kernel with griddepcontrol.wait (pdl_wait()).
+// R2L_ISP_NO_PDL=1 launches plainly (debugging knob).
+bool pdl_enabled();
+bool pdl_enabled_backward();
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(bool allow, void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t st,
+                              Args... args) {
+    if (!allow) {
+        kernel<<<grid, threads, smem, st>>>(KArgs(args)...);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // tensor map over the raw batch: dims (W, H, B), box (box_w, box_h, 2), zero fill outside.
 // false when the shape/pointer does not meet TMA's 16-byte rules (then a non-TMA kernel runs)
 bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_bytes, int B, int H, int W, int box_w, int box_h);

@@ -1,8 +1,11 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4]: ISP throughput sweep -- static (frozen, forward only) vs parametrized (forward + backward),
-256^2 .. 4096^2 synthetic Bayer frames, on one B200.  Prints one JSON line per point: Mpixel/s, achieved GB/s from
-the algorithmic bytes and the fraction of the measured HBM peak.  Working sets are kept above the L2
-(rotating buffer sets).  Kernel-level timing through the C ABI with CUDA events."""
+256^2 .. 4096^2 synthetic Bayer frames, on N B200s (one process per GPU under torchrun, the frames sharded: every rank
+runs the same per-GPU batch, weak scaling, no collective on the data path).  Prints one JSON line per point: aggregate
+Mpixel/s (max time over ranks), achieved GB/s per GPU from the algorithmic bytes and the fraction of the
+measured HBM peak.  Working sets are kept above the L2 (rotating buffer sets).  Kernel-level timing through the C ABI
+with CUDA events.
+usage: python scripts/sweep.py   |   python -m torch.distributed.run --nproc-per-node N scripts/sweep.py"""
 import ctypes
 import json
 import os
@@ -17,7 +20,12 @@ from processing.pipeline_torch import ParametrizedProcessing  # noqa: E402
 
 
 def main():
-    dev = torch.device("cuda:0")
+    import torch.distributed as dist
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -55,13 +63,20 @@ def main():
             for i in range(warm):
                 _lib.check(fn(i % S), "kernel")
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i in range(n):
                 fn(i % S)
             e1.record()
             torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / n
+            ms = e0.elapsed_time(e1) / n
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = t.item()
+            return ms
 
         t_fs = time_it(lambda s: fwd(s, False))
         t_f = time_it(fwd)
@@ -70,11 +85,15 @@ def main():
         for mode, ms, bpp in (("static: forward only", t_fs, 16), ("parametrized: forward + backward (raw grad)", t_f + t_b, 36),
                               ("parametrized: forward + backward (no raw grad)", t_f + t_bn, 32)):
             gbs = bpp * pix / (ms * 1e-3) / 1e9
-            print(json.dumps({"size": size, "batch": B, "mode": mode, "ms": round(ms, 4),
-                              "mpixel_per_s": round(pix / (ms * 1e-3) / 1e6, 1), "algorithmic_bytes_per_px": bpp,
-                              "achieved_gbs": round(gbs, 1), "frac_of_measured_hbm": round(gbs / peak, 4)}), flush=True)
+            if rank == 0:
+                print(json.dumps({"n_gpus": world, "size": size, "batch_per_gpu": B, "mode": mode, "ms": round(ms, 4),
+                                  "mpixel_per_s": round(world * pix / (ms * 1e-3) / 1e6, 1), "algorithmic_bytes_per_px": bpp,
+                                  "achieved_gbs_per_gpu": round(gbs, 1), "frac_of_measured_hbm": round(gbs / peak, 4)}),
+                      flush=True)
         del raws, outs, gouts, graws
         torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
