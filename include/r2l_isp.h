@@ -184,6 +184,38 @@ int r2l_isp_mosaic(const void* raw, int raw_dtype, float raw_denominator, int B,
 int r2l_isp_mosaic_backward(const float* grad_out, int B, int H, int W, int reduce_size, int out_channels,
                             float* grad_raw, void* stream);
 
+/* ---- SSIM regulariser of adversarial training ------------------------------------------------------
+ * Replaces utils/ssim.py:19-39 (`_ssim`: five grouped 11x11 Gaussian-window convolutions with zero padding 5 on
+ * img1, img2, img1^2, img2^2, img1*img2, the SSIM map and its mean), called as SSIM(window_size=11) by train.py:261-262
+ * through AuxLoss (utils/base.py:346-358).  img1 / img2: (B, C, H, W) float32, contiguous.  window_size must be 11
+ * (sigma 1.5, the reference's only use); R2L_ERR_BAD_ARGUMENT otherwise.
+ * forward: partial receives r2l_isp_ssim_partial_count() doubles, the sums of the SSIM map over the 32x32 tiles laid
+ *   out [B][C][tiles]: their total / (B*C*H*W) is `ssim_map.mean()` (:36), the per-image totals / (C*H*W) the
+ *   size_average=False result (:38).
+ * backward: grad1 / grad2 (either may be NULL) receive d(result)/d(img1) / d(img2) for an upstream gradient given as
+ *   scale[b] = grad_result[b] / (number of averaged elements), B floats on the device.  Nothing is kept between the
+ *   two calls: the backward recomputes the window moments. */
+size_t r2l_isp_ssim_partial_count(int B, int C, int H, int W);
+int r2l_isp_ssim_forward(const float* img1, const float* img2, int B, int C, int H, int W, int window_size,
+                         double* partial, void* stream);
+int r2l_isp_ssim_backward(const float* img1, const float* img2, const float* scale, int B, int C, int H, int W,
+                          int window_size, float* grad1, float* grad2, void* stream);
+
+/* ---- numpy-compatible static pipeline --------------------------------------------------------------
+ * Replaces processing/pipeline_numpy.py:70-141 `processing(img, black_level, white_balance, colour_matrix,
+ * debayer='bilinear', sharpening=..., denoising=..., gamma=2.2)` -- the per-image chain of --processing_mode static
+ * (RawProcessingPipeline.__call__, :56-68; 16 DataLoader workers, train.py:316-320) -- for a whole batch in one kernel,
+ * with that chain's boundary rules (scipy half-sample reflection for the bilinear demosaic and the Gaussian filter, zero
+ * fill for the sharpening filter) and its clip to [0, 1].  Forward only.
+ *   black_level[4], white_balance[3], colour_matrix[9]: HOST arrays (camera constants, not trainable here)
+ *   sharpening_filter: 1 = the 3x3 sharpening filter of :178-191, 0 = none
+ *   gaussian_denoising: 1 = scipy.ndimage.gaussian_filter(Y, gaussian_sigma) (:203-209; radius int(4 sigma + 0.5) <= 2), 0 = none
+ *   out (B, 3, H, W) float32. */
+int r2l_isp_numpy_forward(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
+                          const float* black_level, const float* white_balance, const float* colour_matrix,
+                          int sharpening_filter, int gaussian_denoising, float gaussian_sigma, float gamma,
+                          float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,8 @@ EPOCH_DEVICE = 0xFFFFFFFF   # R2L_EPOCH_DEVICE: the kernel keeps the exchange ep
 EXPORTS = ("r2l_isp_abi_version", "r2l_isp_error_string", "r2l_isp_last_cuda_error", "r2l_isp_forward",
            "r2l_isp_workspace_bytes", "r2l_isp_forward_bn_train", "r2l_isp_bn_backward_prepare", "r2l_isp_backward",
            "r2l_isp_mosaic", "r2l_isp_mosaic_backward", "r2l_isp_batch_sum", "r2l_isp_saved_luma_floats",
-           "r2l_isp_luma_supported", "r2l_isp_exchange_bytes", "r2l_isp_backward_dp")
+           "r2l_isp_luma_supported", "r2l_isp_exchange_bytes", "r2l_isp_backward_dp", "r2l_isp_ssim_partial_count",
+           "r2l_isp_ssim_forward", "r2l_isp_ssim_backward", "r2l_isp_numpy_forward")
 
 
 class IspAllreduce(ctypes.Structure):
@@ -87,6 +88,15 @@ def load():
     lib.r2l_isp_mosaic_backward.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp]
     lib.r2l_isp_batch_sum.restype = ci
     lib.r2l_isp_batch_sum.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.r2l_isp_numpy_forward.restype = ci
+    lib.r2l_isp_numpy_forward.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(cf), ctypes.POINTER(cf), ctypes.POINTER(cf),
+                                          ci, ci, cf, cf, vp, vp]
+    lib.r2l_isp_ssim_partial_count.restype = sz
+    lib.r2l_isp_ssim_partial_count.argtypes = [ci, ci, ci, ci]
+    lib.r2l_isp_ssim_forward.restype = ci
+    lib.r2l_isp_ssim_forward.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp]
+    lib.r2l_isp_ssim_backward.restype = ci
+    lib.r2l_isp_ssim_backward.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     if lib.r2l_isp_abi_version() != ABI_VERSION:
         raise ImportError(f"{path}: ABI version {lib.r2l_isp_abi_version()} != expected {ABI_VERSION}; rebuild")
     _LIB = lib

@@ -292,6 +292,96 @@ Tensor batch_sum_cuda(const Tensor& x, const optional<Tensor>& scale) {
     return out;
 }
 
+// ---- numpy-compatible static pipeline (processing/pipeline_numpy.py:70-141), forward only ------------------------------
+Tensor numpy_forward_cuda(const Tensor& raw_, std::vector<double> black_level, std::vector<double> white_balance,
+                          std::vector<double> colour_matrix, bool sharpening_filter, bool gaussian_denoising,
+                          double gaussian_sigma, double gamma, double raw_denominator) {
+    TORCH_CHECK(raw_.dim() == 3, "needs dims (B, H, W), got ", raw_.sizes());
+    TORCH_CHECK(black_level.size() == 4 && white_balance.size() == 3 && colour_matrix.size() == 9,
+                "camera parameters: black_level[4], white_balance[3], colour_matrix[9]");
+    const int b = (int)raw_.size(0), h = (int)raw_.size(1), w = (int)raw_.size(2);
+    int code;
+    Tensor raw = raw_input(raw_, code);
+    c10::cuda::CUDAGuard guard(raw.device());
+    float bl[4], wb[3], ccm[9];
+    for (int i = 0; i < 4; ++i) bl[i] = (float)black_level[i];
+    for (int i = 0; i < 3; ++i) wb[i] = (float)white_balance[i];
+    for (int i = 0; i < 9; ++i) ccm[i] = (float)colour_matrix[i];
+    Tensor out = at::empty({b, 3, h, w}, raw.options().dtype(at::kFloat));
+    check_rc(r2l_isp_numpy_forward(raw.data_ptr(), code, (float)raw_denominator, b, h, w, bl, wb, ccm, (int)sharpening_filter,
+                                   (int)gaussian_denoising, (float)gaussian_sigma, (float)gamma, out.data_ptr<float>(),
+                                   cur_stream(raw)),
+             "r2l_isp_numpy_forward");
+    return out;
+}
+
+// ---- SSIM (utils/ssim.py:19-39): value from the per-tile partial sums, image gradients from the fused backward ----------
+Tensor ssim_forward_cuda(const Tensor& img1, const Tensor& img2, int64_t window_size, bool size_average) {
+    TORCH_CHECK(img1.dim() == 4 && img1.sizes() == img2.sizes(), "ssim needs two (B, C, H, W) tensors of one shape, got ",
+                img1.sizes(), " and ", img2.sizes());
+    const int b = (int)img1.size(0), c = (int)img1.size(1), h = (int)img1.size(2), w = (int)img1.size(3);
+    c10::cuda::CUDAGuard guard(img1.device());
+    Tensor x1 = f32c(img1, img1.numel(), "img1"), x2 = f32c(img2, img2.numel(), "img2");
+    const int64_t tiles = b > 0 ? (int64_t)r2l_isp_ssim_partial_count(b, c, h, w) / ((int64_t)b * c) : 0;
+    Tensor partial = at::empty({b, c * tiles}, x1.options().dtype(at::kDouble));
+    check_rc(r2l_isp_ssim_forward(x1.data_ptr<float>(), x2.data_ptr<float>(), b, c, h, w, (int)window_size,
+                                  partial.data_ptr<double>(), cur_stream(x1)),
+             "r2l_isp_ssim_forward");
+    const double per_image = (double)c * h * w;
+    if (size_average) return (partial.sum() / (per_image * b)).to(at::kFloat);                    // ssim_map.mean()  :36
+    return (partial.sum(1) / per_image).to(at::kFloat);                                            // per image       :38
+}
+
+std::tuple<Tensor, Tensor> ssim_backward_cuda(const Tensor& grad, const Tensor& img1, const Tensor& img2,
+                                              int64_t window_size, bool size_average, bool need1, bool need2) {
+    const int b = (int)img1.size(0), c = (int)img1.size(1), h = (int)img1.size(2), w = (int)img1.size(3);
+    c10::cuda::CUDAGuard guard(img1.device());
+    Tensor x1 = f32c(img1, img1.numel(), "img1"), x2 = f32c(img2, img2.numel(), "img2");
+    const double per_image = (double)c * h * w;
+    Tensor scale = size_average ? (grad.to(at::kFloat).reshape({1}) / (per_image * b)).expand({b}).contiguous()
+                                : (grad.to(at::kFloat).reshape({b}) / per_image).contiguous();
+    Tensor g1 = need1 ? at::empty_like(x1) : Tensor(), g2 = need2 ? at::empty_like(x2) : Tensor();
+    check_rc(r2l_isp_ssim_backward(x1.data_ptr<float>(), x2.data_ptr<float>(), scale.data_ptr<float>(), b, c, h, w,
+                                   (int)window_size, need1 ? g1.data_ptr<float>() : nullptr,
+                                   need2 ? g2.data_ptr<float>() : nullptr, cur_stream(x1)),
+             "r2l_isp_ssim_backward");
+    return {need1 ? g1 : at::empty({0}, x1.options()), need2 ? g2 : at::empty({0}, x1.options())};
+}
+
+struct SsimFn : public torch::autograd::Function<SsimFn> {
+    static Tensor forward(torch::autograd::AutogradContext* ctx, const Tensor& img1, const Tensor& img2, int64_t window_size,
+                          bool size_average) {
+        at::AutoDispatchBelowADInplaceOrView guard;
+        static auto op = c10::Dispatcher::singleton().findSchemaOrThrow("raw2logit_isp::ssim_forward", "")
+                             .typed<decltype(ssim_forward_cuda)>();
+        ctx->save_for_backward({img1, img2});
+        ctx->saved_data["window_size"] = window_size;
+        ctx->saved_data["size_average"] = size_average;
+        ctx->saved_data["need1"] = img1.requires_grad();
+        ctx->saved_data["need2"] = img2.requires_grad();
+        return op.call(img1, img2, window_size, size_average);
+    }
+    static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx,
+                                                   torch::autograd::variable_list grad_outputs) {
+        at::AutoDispatchBelowADInplaceOrView guard;
+        static auto op = c10::Dispatcher::singleton().findSchemaOrThrow("raw2logit_isp::ssim_backward", "")
+                             .typed<decltype(ssim_backward_cuda)>();
+        auto sv = ctx->get_saved_variables();
+        const bool need1 = ctx->saved_data["need1"].toBool(), need2 = ctx->saved_data["need2"].toBool();
+        torch::autograd::variable_list grads(4);
+        if (need1 || need2) {
+            auto r = op.call(grad_outputs[0], sv[0], sv[1], ctx->saved_data["window_size"].toInt(),
+                             ctx->saved_data["size_average"].toBool(), need1, need2);
+            if (need1) grads[0] = std::get<0>(r);
+            if (need2) grads[1] = std::get<1>(r);
+        }
+        return grads;
+    }
+};
+Tensor ssim_autograd(const Tensor& img1, const Tensor& img2, int64_t window_size, bool size_average) {
+    return SsimFn::apply(img1, img2, window_size, size_average);
+}
+
 void set_exchange(int64_t world, int64_t rank, int64_t peers, double scale, bool on) {
     std::lock_guard<std::mutex> lock(g_xch_mutex);
     g_xch.on = on; g_xch.world = (int)world; g_xch.rank = (int)rank; g_xch.peers = peers; g_xch.scale = (float)scale;
@@ -519,6 +609,13 @@ TORCH_LIBRARY(raw2logit_isp, m) {
     m.def("fused(Tensor raw, " R2L_PARAMS_SCHEMA ", Tensor? additive, int bn_mode, Tensor(a!)? running_mean, "
           "Tensor(b!)? running_var, float momentum, float eps, float raw_denominator) -> Tensor");
     m.def("mosaic_ad(Tensor raw, Tensor? black_level, bool reduce_size, int out_channels, float raw_denominator) -> Tensor");
+    m.def("numpy_forward(Tensor raw, float[] black_level, float[] white_balance, float[] colour_matrix, bool sharpening_filter, "
+          "bool gaussian_denoising, float gaussian_sigma, float gamma, float raw_denominator) -> Tensor");
+    // SSIM regulariser (utils/ssim.py): plain ops + the differentiable entry point
+    m.def("ssim_forward(Tensor img1, Tensor img2, int window_size, bool size_average) -> Tensor");
+    m.def("ssim_backward(Tensor grad, Tensor img1, Tensor img2, int window_size, bool size_average, bool need1, "
+          "bool need2) -> (Tensor, Tensor)");
+    m.def("ssim(Tensor img1, Tensor img2, int window_size, bool size_average) -> Tensor");
     // process-wide state of the fused data-parallel exchange (parallel.enable_fused_gradient_exchange)
     m.def("set_exchange(int world, int rank, int peers, float scale, bool on) -> ()", &set_exchange);
 }
@@ -532,10 +629,15 @@ TORCH_LIBRARY_IMPL(raw2logit_isp, CUDA, m) {
     m.impl("mosaic_backward", &mosaic_backward_cuda);
     m.impl("batch_sum", &batch_sum_cuda);
     m.impl("fused", &fused_cuda);
+    m.impl("numpy_forward", &numpy_forward_cuda);
+    m.impl("ssim_forward", &ssim_forward_cuda);
+    m.impl("ssim_backward", &ssim_backward_cuda);
+    m.impl("ssim", &ssim_forward_cuda);
     m.impl("mosaic_ad", &mosaic_cuda);
 }
 
 TORCH_LIBRARY_IMPL(raw2logit_isp, Autograd, m) {
     m.impl("fused", &fused_autograd);
     m.impl("mosaic_ad", &mosaic_autograd);
+    m.impl("ssim", &ssim_autograd);
 }
