@@ -70,29 +70,6 @@ struct Bwd5Acc { float sums[kBwd5AccFloats]; };
 #endif
 
 #ifndef R2L_HOST_EMU
-// ---- ticket of the fused finish: one 64-bit word {count (low), generation (high)} in the workspace.  A launch owns the
-// word once its generation tag is in it: whatever the word held before (an uninitialised workspace, the previous
-// launch's final count) is replaced by {gen, 0} by the first CTA to arrive -- no memset in front of the kernel (which
-// would also sit between this kernel and the one before it on the stream), no zero-fill contract.  The last CTA clears
-// the word, so a captured launch (same tag at every replay) starts clean as well.
-// Returns this CTA's ticket 0 .. n_cta-1.  The count itself is ONE atomic add per CTA (a compare-and-swap loop here made
-// the 160 CTAs that finish their third tile together retry against each other: +86 us at 64 x 256 x 256,
-// profiles/r02_summary.md); only a CTA that finds a foreign tag makes one compare-and-swap attempt to install this
-// launch's tag first -- if that fails, another CTA of this launch has installed it.
-__device__ __forceinline__ unsigned take_ticket(unsigned* ticket, unsigned gen) {
-    unsigned long long* w = reinterpret_cast<unsigned long long*>(ticket);
-    volatile unsigned long long* vw = reinterpret_cast<volatile unsigned long long*>(w);
-    unsigned long long cur = *vw;
-    if ((unsigned)(cur >> 32) != gen) {
-        atomicCAS(w, cur, (unsigned long long)gen << 32);
-        do { cur = *vw; } while ((unsigned)(cur >> 32) != gen);
-    }
-    return (unsigned)atomicAdd(w, 1ull);
-}
-__device__ __forceinline__ void clear_ticket(unsigned* ticket) {
-    *reinterpret_cast<volatile unsigned long long*>(ticket) = 0ull;
-}
-
 // ---- one-shot all-reduce of the 132 gradients over NVLink peer memory, run by the CTA that finished them ------------
 // (r2l_isp_backward_dp, include/r2l_isp.h).  Every gradient travels as one 8-byte word {value, epoch} written by ONE
 // 64-bit store (single-copy atomic), so the epoch tag tells the reader that the value next to it is this step's -- no

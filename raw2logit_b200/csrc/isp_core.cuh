@@ -316,6 +316,17 @@ struct FwdArgs {
     float* chan_partials;      // STATS only: [n_cta][kChanPitch] per-CTA sums of o and o*o per channel
     float* luma = nullptr;     // null, or [2][ceil(B/2)][H][W][2]: Y0 (plane 0) and Y1 (plane 1) of image pairs
                                // (2p, 2p+1) interleaved per site, saved for the fourth-generation backward
+    // Fused train-mode BatchNorm tail (STATS kernels of the third generation, device only).  With bn_sync set the launch
+    // finishes the batch statistics itself behind a grid-wide barrier -- every CTA reduces the per-CTA channel sums in
+    // the same fixed order -- writes saved_affine / the running statistics (CTA 0) and normalises the tiles it wrote
+    // while their lines are still in L2: one launch instead of three (forward, finish, in-place normalisation).
+    unsigned* bn_sync = nullptr;           // two 8-byte ticket words {count, launch tag}: arrive, depart
+    unsigned bn_gen = 0;                   // launch tag (never 0)
+    double bn_count = 0.0;                 // B * H * W
+    float bn_momentum = 0.f, bn_eps = 0.f;
+    float* bn_running_mean = nullptr;      // may be null
+    float* bn_running_var = nullptr;       // may be null
+    float* bn_saved_affine = nullptr;      // {1/sqrt(var+eps)[3], -mean/sqrt(var+eps)[3]}
 };
 constexpr int kChanPitch = 8;
 

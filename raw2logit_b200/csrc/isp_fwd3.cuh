@@ -407,6 +407,95 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
             for (int w = 0; w < NW; ++w) sum += red[w * 6 + tid];
             part[tid] = sum;
         }
+        if (a.bn_sync) {
+            // ---- fused BatchNorm tail (FwdArgs::bn_sync): grid-wide barrier, statistics, normalisation of own tiles --------
+            // Every CTA of the persistent grid is resident (or becomes so as the kernel before this one drains), so
+            // waiting for all of them cannot deadlock.  arrive: the channel sums above are visible device-wide first.
+            __shared__ float s_aff[6];
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                take_ticket(a.bn_sync, a.bn_gen);
+                const volatile unsigned long long* w = reinterpret_cast<const volatile unsigned long long*>(a.bn_sync);
+                for (;;) {
+                    const unsigned long long v = *w;
+                    if ((unsigned)(v >> 32) == a.bn_gen && (unsigned)v >= (unsigned)n_cta) break;
+                    __nanosleep(64);
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            // batch mean / biased variance per channel: one warp per channel, lanes stride over the per-CTA sums, fp64,
+            // fixed order -- the same arithmetic in every CTA (and as bn_finish_kernel), so all CTAs normalise alike
+            if (warp < 3) {
+                const int c = warp;
+                double s1 = 0.0, s2 = 0.0;
+                for (int i = lane; i < n_cta; i += 32) {
+                    s1 += (double)__ldcg(a.chan_partials + (size_t)i * kChanPitch + c);
+                    s2 += (double)__ldcg(a.chan_partials + (size_t)i * kChanPitch + 3 + c);
+                }
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                if (lane == 0) {
+                    const double mean = s1 / a.bn_count;
+                    double var = s2 / a.bn_count - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    const double inv = 1.0 / sqrt(var + (double)a.bn_eps);
+                    s_aff[c] = (float)inv;
+                    s_aff[3 + c] = (float)(-mean * inv);
+                    if (cta == 0) {
+                        a.bn_saved_affine[c] = (float)inv;
+                        a.bn_saved_affine[3 + c] = (float)(-mean * inv);
+                        const double m = (double)a.bn_momentum;
+                        if (a.bn_running_mean) a.bn_running_mean[c] = (float)((1.0 - m) * (double)a.bn_running_mean[c] + m * mean);
+                        if (a.bn_running_var) {
+                            const double unbiased = a.bn_count > 1.0 ? var * a.bn_count / (a.bn_count - 1.0) : var;
+                            a.bn_running_var[c] = (float)((1.0 - m) * (double)a.bn_running_var[c] + m * unbiased);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // normalise, in place, exactly the tiles this CTA produced (128-bit accesses; L2-only loads: the lines were
+            // written by this CTA a few microseconds ago)
+            for (int tile = cta; tile < grid.n; tile += n_cta) {
+                int b0, b1, ty0, tx0;
+                decode_pair_tile(grid, tile, TH, TW, a.B, b0, b1, ty0, tx0);
+                const int rows = imin(TH, H - ty0), runs = imin(G, (W - tx0) >> 2);
+                const int n_img = b1 == b0 ? 1 : 2;
+                static_assert((TH * G) % NT == 0 && (G & (G - 1)) == 0, "whole passes over the tile, shift / mask indexing");
+                // (image, channel) planes outermost, a tile plane = TH x G runs of four sites: no division in the loop
+                for (int pl = 0; pl < 3 * n_img; ++pl) {
+                    const int im = pl >= 3 ? 1 : 0, k = pl - 3 * im;
+                    const float sc = s_aff[k], sh = s_aff[3 + k];
+                    float* base = a.out + ((size_t)(b0 + im) * 3 + k) * plane + (size_t)ty0 * W + tx0;
+                    float4 v[TH * G / NT];
+#pragma unroll
+                    for (int u = 0; u < TH * G / NT; ++u) {
+                        const int i = tid + u * NT, rr = i / G, g = i & (G - 1);
+                        if (rr < rows && g < runs) v[u] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)rr * W) + g);
+                    }
+#pragma unroll
+                    for (int u = 0; u < TH * G / NT; ++u) {
+                        const int i = tid + u * NT, rr = i / G, g = i & (G - 1);
+                        if (rr < rows && g < runs) {
+                            float4 t = v[u];
+                            t.x = fmaf(t.x, sc, sh); t.y = fmaf(t.y, sc, sh); t.z = fmaf(t.z, sc, sh); t.w = fmaf(t.w, sc, sh);
+                            reinterpret_cast<float4*>(base + (size_t)rr * W)[g] = t;
+                        }
+                    }
+                }
+            }
+            // depart: the last CTA to leave clears both ticket words (a captured launch replays with the same tag)
+            __syncthreads();
+            if (tid == 0 && take_ticket(a.bn_sync + 2, a.bn_gen) == (unsigned)n_cta - 1u) {
+                clear_ticket(a.bn_sync);
+                clear_ticket(a.bn_sync + 2);
+            }
+        }
 #endif
     }
 }

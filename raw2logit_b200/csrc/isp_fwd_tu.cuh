@@ -58,14 +58,18 @@ static int launch_forward3_t(const FwdArgs& a, cudaStream_t st, int* grid_used) 
 }
 
 template <typename RawT>
-static int launch_forward_impl(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used) {
+static int launch_forward_impl(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used, bool* fused_tail) {
+    if (fused_tail) *fused_tail = false;
     const char* force = getenv("R2L_ISP_FORCE_GENERIC");            // debugging knob: second-generation kernel
     if (!(force && force[0] == '1') && fwd3_shape_ok(a.H, a.W) && aligned(a.out, 16) && aligned(a.additive, 16)) {
         int rc;
         if (stats) rc = launch_forward3_t<Fwd3Default, RawT, true, false>(a, st, grid_used);
         else if (a.additive || a.affine) rc = launch_forward3_t<Fwd3Default, RawT, false, true>(a, st, grid_used);
         else rc = launch_forward3_t<Fwd3Default, RawT, false, false>(a, st, grid_used);
-        if (rc != kNotServed) return rc;
+        if (rc != kNotServed) {
+            if (fused_tail) *fused_tail = rc == R2L_OK && stats && a.bn_sync != nullptr;
+            return rc;
+        }
     }
     return stats ? launch_forward_t<Fwd2Default, RawT, true>(a, st, grid_used)
                  : launch_forward_t<Fwd2Default, RawT, false>(a, st, grid_used);

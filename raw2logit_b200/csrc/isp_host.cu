@@ -453,8 +453,10 @@ static int launch_finish(const BwdArgs& a, int n_cta, float* grads, cudaStream_t
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);
 }
 
-static int launch_forward_any(const FwdArgs& a, int raw_dtype, bool stats, cudaStream_t st, int* grid_used) {
-    return raw_dtype == R2L_F32 ? launch_forward_f32(a, stats, st, grid_used) : launch_forward_u16(a, stats, st, grid_used);
+static int launch_forward_any(const FwdArgs& a, int raw_dtype, bool stats, cudaStream_t st, int* grid_used,
+                              bool* fused_tail = nullptr) {
+    return raw_dtype == R2L_F32 ? launch_forward_f32(a, stats, st, grid_used, fused_tail)
+                                : launch_forward_u16(a, stats, st, grid_used, fused_tail);
 }
 
 // vectorised third-generation kernel when the shape / alignment allows, generic scalar kernel otherwise
@@ -558,9 +560,20 @@ int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominat
     a.additive = additive; a.affine = nullptr; a.out = out; a.chan_partials = static_cast<float*>(workspace);
     a.luma = saved_luma;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the third-generation kernel finishes the statistics and normalises its tiles itself (one launch); the ticket words
+    // of its grid-wide barrier sit behind the backward's ticket in the workspace
+    const char* split = getenv("R2L_ISP_BN_SPLIT");             // debugging knob: the three-launch path
+    if (!(split && split[0] == '1')) {
+        a.bn_sync = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + kTicketOffset + 64);
+        a.bn_gen = next_ticket_generation();
+        a.bn_count = (double)B * H * W; a.bn_momentum = momentum; a.bn_eps = eps;
+        a.bn_running_mean = running_mean; a.bn_running_var = running_var; a.bn_saved_affine = saved_affine;
+    }
     int g = 0;
-    rc = launch_forward_any(a, raw_dtype, true, st, &g);
+    bool fused = false;
+    rc = launch_forward_any(a, raw_dtype, true, st, &g, &fused);
     if (rc != R2L_OK) return rc;
+    if (fused) return R2L_OK;
     bn_finish_kernel<<<1, 96, 0, st>>>(a.chan_partials, g, (double)B * H * W, momentum, eps, running_mean,
                                        running_var, saved_affine);
     cudaError_t e = cudaGetLastError();

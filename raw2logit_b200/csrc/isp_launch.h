@@ -67,8 +67,9 @@ static cudaError_t launch_pdl(bool allow, void (*kernel)(KArgs...), int grid, in
 bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_bytes, int B, int H, int W, int box_w, int box_h);
 
 // launchers, one translation unit each (compiled in parallel by _build.py)
-int launch_forward_f32(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used);
-int launch_forward_u16(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used);
+// *fused_tail (may be null): the launch ran the fused train-mode BatchNorm tail itself (FwdArgs::bn_sync, third generation)
+int launch_forward_f32(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used, bool* fused_tail = nullptr);
+int launch_forward_u16(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used, bool* fused_tail = nullptr);
 // third-generation backward (TMA-fed); returns kNotServed when the shape / alignment is not served
 int launch_backward3_f32(const BwdArgs& a, cudaStream_t st, int* grid_used);
 int launch_backward3_u16(const BwdArgs& a, cudaStream_t st, int* grid_used);
