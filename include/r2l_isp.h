@@ -201,6 +201,17 @@ int r2l_isp_ssim_forward(const float* img1, const float* img2, int B, int C, int
 int r2l_isp_ssim_backward(const float* img1, const float* img2, const float* scale, int B, int C, int H, int W,
                           int window_size, float* grad1, float* grad2, void* stream);
 
+/* ---- augmentation + hand-off to the task model in one pass -----------------------------------------
+ * Replaces the chain  augmentation_weak (utils/augmentation.py:70-74: RandomHorizontalFlip, RandomVerticalFlip,
+ * RandomRotate90 :8-11; applied at model.py:79-82)  ->  .contiguous(memory_format=channels_last)  ->  .to(bfloat16):
+ * dst[b][c][y][x] = src[b][c][a0 + a1 y + a2 x][b0 + b1 y + b2 x]  for a dihedral map6 = {a0, a1, a2, b0, b1, b2} (the
+ * composition of the drawn flips / quarter turns, formed by the host), both tensors addressed through element strides
+ * {batch, channel, row, column} (NCHW, channels_last, ...) and dtype codes 0 = float32, 2 = bfloat16 (round to nearest
+ * even, like Tensor.to).  The adjoint is the same call with the inverse map and the gradient as source.  C <= 4. */
+int r2l_isp_dihedral_copy(const void* src, int src_dtype, const long long* src_strides, void* dst, int dst_dtype,
+                          const long long* dst_strides, int B, int C, int H_dst, int W_dst, int H_src, int W_src,
+                          const int* map6, void* stream);
+
 /* ---- numpy-compatible static pipeline --------------------------------------------------------------
  * Replaces processing/pipeline_numpy.py:70-141 `processing(img, black_level, white_balance, colour_matrix,
  * debayer='bilinear', sharpening=..., denoising=..., gamma=2.2)` -- the per-image chain of --processing_mode static

@@ -25,7 +25,7 @@ EXPORTS = ("r2l_isp_abi_version", "r2l_isp_error_string", "r2l_isp_last_cuda_err
            "r2l_isp_workspace_bytes", "r2l_isp_forward_bn_train", "r2l_isp_bn_backward_prepare", "r2l_isp_backward",
            "r2l_isp_mosaic", "r2l_isp_mosaic_backward", "r2l_isp_batch_sum", "r2l_isp_saved_luma_floats",
            "r2l_isp_luma_supported", "r2l_isp_exchange_bytes", "r2l_isp_backward_dp", "r2l_isp_ssim_partial_count",
-           "r2l_isp_ssim_forward", "r2l_isp_ssim_backward", "r2l_isp_numpy_forward")
+           "r2l_isp_ssim_forward", "r2l_isp_ssim_backward", "r2l_isp_numpy_forward", "r2l_isp_dihedral_copy")
 
 
 class IspAllreduce(ctypes.Structure):
@@ -88,6 +88,9 @@ def load():
     lib.r2l_isp_mosaic_backward.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp]
     lib.r2l_isp_batch_sum.restype = ci
     lib.r2l_isp_batch_sum.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.r2l_isp_dihedral_copy.restype = ci
+    lib.r2l_isp_dihedral_copy.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_longlong), vp, ci, ctypes.POINTER(ctypes.c_longlong),
+                                          ci, ci, ci, ci, ci, ci, ctypes.POINTER(ci), vp]
     lib.r2l_isp_numpy_forward.restype = ci
     lib.r2l_isp_numpy_forward.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(cf), ctypes.POINTER(cf), ctypes.POINTER(cf),
                                           ci, ci, cf, cf, vp, vp]

@@ -292,6 +292,27 @@ Tensor batch_sum_cuda(const Tensor& x, const optional<Tensor>& scale) {
     return out;
 }
 
+// ---- augmentation + hand-off in one pass (utils/augmentation.py:70-74, model.py:79-82): dihedral index map, strides, dtype
+Tensor dihedral_copy_cuda(const Tensor& src, std::vector<int64_t> map6, int64_t h_dst, int64_t w_dst, bool channels_last,
+                          bool to_bf16) {
+    TORCH_CHECK(src.dim() == 4 && src.is_cuda(), "dihedral_copy needs a (B, C, H, W) CUDA tensor");
+    TORCH_CHECK(src.scalar_type() == at::kFloat || src.scalar_type() == at::kBFloat16, "float32 or bfloat16 source, got ",
+                src.scalar_type());
+    TORCH_CHECK(map6.size() == 6, "map6 = {a0, a1, a2, b0, b1, b2}");
+    c10::cuda::CUDAGuard guard(src.device());
+    const int b = (int)src.size(0), c = (int)src.size(1);
+    Tensor dst = at::empty({b, c, h_dst, w_dst}, src.options().dtype(to_bf16 ? at::kBFloat16 : at::kFloat),
+                           channels_last ? at::MemoryFormat::ChannelsLast : at::MemoryFormat::Contiguous);
+    long long ss[4], ds[4];
+    int m[6];
+    for (int i = 0; i < 4; ++i) { ss[i] = src.stride(i); ds[i] = dst.stride(i); }
+    for (int i = 0; i < 6; ++i) m[i] = (int)map6[i];
+    check_rc(r2l_isp_dihedral_copy(src.data_ptr(), src.scalar_type() == at::kFloat ? 0 : 2, ss, dst.data_ptr(), to_bf16 ? 2 : 0, ds,
+                                   b, c, (int)h_dst, (int)w_dst, (int)src.size(2), (int)src.size(3), m, cur_stream(src)),
+             "r2l_isp_dihedral_copy");
+    return dst;
+}
+
 // ---- numpy-compatible static pipeline (processing/pipeline_numpy.py:70-141), forward only ------------------------------
 Tensor numpy_forward_cuda(const Tensor& raw_, std::vector<double> black_level, std::vector<double> white_balance,
                           std::vector<double> colour_matrix, bool sharpening_filter, bool gaussian_denoising,
@@ -609,6 +630,7 @@ TORCH_LIBRARY(raw2logit_isp, m) {
     m.def("fused(Tensor raw, " R2L_PARAMS_SCHEMA ", Tensor? additive, int bn_mode, Tensor(a!)? running_mean, "
           "Tensor(b!)? running_var, float momentum, float eps, float raw_denominator) -> Tensor");
     m.def("mosaic_ad(Tensor raw, Tensor? black_level, bool reduce_size, int out_channels, float raw_denominator) -> Tensor");
+    m.def("dihedral_copy(Tensor src, int[] map6, int h_dst, int w_dst, bool channels_last, bool to_bf16) -> Tensor");
     m.def("numpy_forward(Tensor raw, float[] black_level, float[] white_balance, float[] colour_matrix, bool sharpening_filter, "
           "bool gaussian_denoising, float gaussian_sigma, float gamma, float raw_denominator) -> Tensor");
     // SSIM regulariser (utils/ssim.py): plain ops + the differentiable entry point
@@ -629,6 +651,7 @@ TORCH_LIBRARY_IMPL(raw2logit_isp, CUDA, m) {
     m.impl("mosaic_backward", &mosaic_backward_cuda);
     m.impl("batch_sum", &batch_sum_cuda);
     m.impl("fused", &fused_cuda);
+    m.impl("dihedral_copy", &dihedral_copy_cuda);
     m.impl("numpy_forward", &numpy_forward_cuda);
     m.impl("ssim_forward", &ssim_forward_cuda);
     m.impl("ssim_backward", &ssim_backward_cuda);
