@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define R2L_ABI_VERSION 5
+#define R2L_ABI_VERSION 6
 
 enum {
     R2L_OK = 0,
@@ -226,6 +226,32 @@ int r2l_isp_numpy_forward(const void* raw, int raw_dtype, float raw_denominator,
                           const float* black_level, const float* white_balance, const float* colour_matrix,
                           int sharpening_filter, int gaussian_denoising, float gaussian_sigma, float gamma,
                           float* out, void* stream);
+
+/* ---- staged mode: one kernel per stage of ParametrizedProcessing.forward with track_stages=True ----------------------
+ * Replaces the per-stage torch ops of pipeline_torch.py:183-214 whose outputs the reference keeps in `self.stages`
+ * (and whose .grad model.track_images reads, model.py:229-254).  Every linear stage is a 3 -> 3 channel K x K
+ * correlation of the previous stage's tensor (colour stage :187-191 = CCM.diag(wb).Debayer, K = 3, reflect-1 pad;
+ * sharpening :194-198 = M_yuv2rgb.[sharpen(Y)|U|V].M_rgb2yuv, K = 3, zero pad; Gaussian :199-203, K = 5, reflect-2 pad);
+ * the host forms the combined weight [3][3][K][K] (raw2logit_b200/staged.py).
+ *   r2l_isp_stage_conv:           y[b][co] = sum_ci corr(x_pad[b][ci], weight[co][ci]);  x, y (B, 3, H, W) float32,
+ *                                 K in {3, 5}, pad_mode 0 = zeros, 1 = reflect (R2L_ERR_BAD_SHAPE when H or W <= K/2)
+ *   r2l_isp_stage_conv_backward:  grad_x (nullable) and grad_weight (nullable, 9 K K floats; needs x and a workspace of
+ *                                 r2l_isp_stage_workspace_bytes(K) bytes, 8-byte aligned); deterministic two-stage sums
+ *   r2l_isp_stage_clip(_backward):  y = clamp(x, lo, hi) (:206); grad_x = grad_y where lo <= x <= hi (torch.clip)
+ *   r2l_isp_stage_gamma(_backward): y = exp((1 / gamma) * log(x)) (:209), gamma = one float on the device;
+ *                                 grad_x (nullable) = grad_y y / (gamma x), grad_gamma[0] = -sum(grad_y y log x) / gamma^2;
+ *                                 workspace as above (any K). */
+size_t r2l_isp_stage_workspace_bytes(int K);
+int r2l_isp_stage_conv(const float* x, const float* weight, int B, int H, int W, int K, int pad_mode, float* y, void* stream);
+int r2l_isp_stage_conv_backward(const float* x, const float* weight, const float* grad_y, int B, int H, int W, int K,
+                                int pad_mode, float* grad_x, float* grad_weight, void* workspace, size_t workspace_bytes,
+                                void* stream);
+int r2l_isp_stage_clip(const float* x, long long n, float lo, float hi, float* y, void* stream);
+int r2l_isp_stage_clip_backward(const float* x, const float* grad_y, long long n, float lo, float hi, float* grad_x,
+                                void* stream);
+int r2l_isp_stage_gamma(const float* x, const float* gamma, long long n, float* y, void* stream);
+int r2l_isp_stage_gamma_backward(const float* x, const float* y, const float* grad_y, const float* gamma, long long n,
+                                 float* grad_x, float* grad_gamma, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

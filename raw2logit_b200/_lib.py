@@ -18,14 +18,16 @@ GRAD_LAYOUT = {
     "gauss_weight": (107, 25, (1, 1, 5, 5)),
 }
 F32, U16 = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 EPOCH_DEVICE = 0xFFFFFFFF   # R2L_EPOCH_DEVICE: the kernel keeps the exchange epoch itself (graph-capturable)
 
 EXPORTS = ("r2l_isp_abi_version", "r2l_isp_error_string", "r2l_isp_last_cuda_error", "r2l_isp_forward",
            "r2l_isp_workspace_bytes", "r2l_isp_forward_bn_train", "r2l_isp_bn_backward_prepare", "r2l_isp_backward",
            "r2l_isp_mosaic", "r2l_isp_mosaic_backward", "r2l_isp_batch_sum", "r2l_isp_saved_luma_floats",
            "r2l_isp_luma_supported", "r2l_isp_exchange_bytes", "r2l_isp_backward_dp", "r2l_isp_ssim_partial_count",
-           "r2l_isp_ssim_forward", "r2l_isp_ssim_backward", "r2l_isp_numpy_forward", "r2l_isp_dihedral_copy")
+           "r2l_isp_ssim_forward", "r2l_isp_ssim_backward", "r2l_isp_numpy_forward", "r2l_isp_dihedral_copy",
+           "r2l_isp_stage_workspace_bytes", "r2l_isp_stage_conv", "r2l_isp_stage_conv_backward", "r2l_isp_stage_clip",
+           "r2l_isp_stage_clip_backward", "r2l_isp_stage_gamma", "r2l_isp_stage_gamma_backward")
 
 
 class IspAllreduce(ctypes.Structure):

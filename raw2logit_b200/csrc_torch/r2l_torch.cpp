@@ -403,6 +403,91 @@ Tensor ssim_autograd(const Tensor& img1, const Tensor& img2, int64_t window_size
     return SsimFn::apply(img1, img2, window_size, size_average);
 }
 
+// ---- staged mode (track_stages=True, pipeline_torch.py:183-221): one repo kernel per stage (csrc/isp_stages.cu); the
+// autograd nodes that string them together are Python (raw2logit_b200/staged.py) -- an inspection path, a few images per epoch
+void stage_dims(const Tensor& x, const Tensor& weight, int& b, int& h, int& w, int& k) {
+    TORCH_CHECK(x.dim() == 4 && x.size(1) == 3, "stage_conv needs a (B, 3, H, W) tensor, got ", x.sizes());
+    TORCH_CHECK(weight.dim() == 4 && weight.size(0) == 3 && weight.size(1) == 3 && weight.size(2) == weight.size(3),
+                "stage_conv needs a (3, 3, K, K) weight, got ", weight.sizes());
+    b = (int)x.size(0); h = (int)x.size(2); w = (int)x.size(3); k = (int)weight.size(2);
+}
+Tensor stage_scratch(const Tensor& like, int k, size_t& nbytes) {
+    nbytes = r2l_isp_stage_workspace_bytes(k);
+    return at::empty({(int64_t)(nbytes / 8)}, like.options().dtype(at::kDouble));
+}
+Tensor stage_conv_cuda(const Tensor& x, const Tensor& weight, bool reflect) {
+    int b, h, w, k;
+    stage_dims(x, weight, b, h, w, k);
+    // the reference fails inside F.pad / the conv's reflect padding for frames this small
+    TORCH_CHECK(!reflect || (h > k / 2 && w > k / 2), "Padding size should be less than the corresponding input dimension, got H=",
+                h, ", W=", w);
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor xc = f32c(x, x.numel(), "x"), wc = f32c(weight, 9 * k * k, "weight");
+    Tensor y = at::empty_like(xc);
+    check_rc(r2l_isp_stage_conv(xc.data_ptr<float>(), wc.data_ptr<float>(), b, h, w, k, reflect ? 1 : 0, y.data_ptr<float>(),
+                                cur_stream(xc)),
+             "r2l_isp_stage_conv");
+    return y;
+}
+std::tuple<Tensor, Tensor> stage_conv_backward_cuda(const Tensor& x, const Tensor& weight, const Tensor& grad_y, bool reflect,
+                                                    bool need_x, bool need_w) {
+    int b, h, w, k;
+    stage_dims(x, weight, b, h, w, k);
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor xc = f32c(x, x.numel(), "x"), wc = f32c(weight, 9 * k * k, "weight"), gc = f32c(grad_y, x.numel(), "grad_y");
+    Tensor gx = need_x ? at::empty_like(xc) : at::empty({0}, xc.options());
+    Tensor gw = need_w ? at::empty({3, 3, k, k}, xc.options()) : at::empty({0}, xc.options());
+    size_t nbytes = 0;
+    Tensor ws = stage_scratch(xc, k, nbytes);
+    check_rc(r2l_isp_stage_conv_backward(xc.data_ptr<float>(), wc.data_ptr<float>(), gc.data_ptr<float>(), b, h, w, k,
+                                         reflect ? 1 : 0, need_x ? gx.data_ptr<float>() : nullptr,
+                                         need_w ? gw.data_ptr<float>() : nullptr, ws.data_ptr(), nbytes, cur_stream(xc)),
+             "r2l_isp_stage_conv_backward");
+    return {gx, gw};
+}
+Tensor stage_clip_cuda(const Tensor& x, double lo, double hi) {
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor xc = f32c(x, x.numel(), "x");
+    Tensor y = at::empty_like(xc);
+    check_rc(r2l_isp_stage_clip(xc.data_ptr<float>(), (long long)xc.numel(), (float)lo, (float)hi, y.data_ptr<float>(),
+                                cur_stream(xc)),
+             "r2l_isp_stage_clip");
+    return y;
+}
+Tensor stage_clip_backward_cuda(const Tensor& x, const Tensor& grad_y, double lo, double hi) {
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor xc = f32c(x, x.numel(), "x"), gc = f32c(grad_y, x.numel(), "grad_y");
+    Tensor gx = at::empty_like(xc);
+    check_rc(r2l_isp_stage_clip_backward(xc.data_ptr<float>(), gc.data_ptr<float>(), (long long)xc.numel(), (float)lo, (float)hi,
+                                         gx.data_ptr<float>(), cur_stream(xc)),
+             "r2l_isp_stage_clip_backward");
+    return gx;
+}
+Tensor stage_gamma_cuda(const Tensor& x, const Tensor& gamma) {
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor xc = f32c(x, x.numel(), "x"), gm = f32c(gamma, 1, "gamma");
+    Tensor y = at::empty_like(xc);
+    check_rc(r2l_isp_stage_gamma(xc.data_ptr<float>(), gm.data_ptr<float>(), (long long)xc.numel(), y.data_ptr<float>(),
+                                 cur_stream(xc)),
+             "r2l_isp_stage_gamma");
+    return y;
+}
+std::tuple<Tensor, Tensor> stage_gamma_backward_cuda(const Tensor& x, const Tensor& y, const Tensor& grad_y, const Tensor& gamma,
+                                                     bool need_x) {
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor xc = f32c(x, x.numel(), "x"), yc = f32c(y, x.numel(), "y"), gc = f32c(grad_y, x.numel(), "grad_y");
+    Tensor gm = f32c(gamma, 1, "gamma");
+    Tensor gx = need_x ? at::empty_like(xc) : at::empty({0}, xc.options());
+    Tensor gg = at::empty({1}, xc.options());
+    size_t nbytes = 0;
+    Tensor ws = stage_scratch(xc, 3, nbytes);
+    check_rc(r2l_isp_stage_gamma_backward(xc.data_ptr<float>(), yc.data_ptr<float>(), gc.data_ptr<float>(), gm.data_ptr<float>(),
+                                          (long long)xc.numel(), need_x ? gx.data_ptr<float>() : nullptr, gg.data_ptr<float>(),
+                                          ws.data_ptr(), nbytes, cur_stream(xc)),
+             "r2l_isp_stage_gamma_backward");
+    return {gx, gg};
+}
+
 void set_exchange(int64_t world, int64_t rank, int64_t peers, double scale, bool on) {
     std::lock_guard<std::mutex> lock(g_xch_mutex);
     g_xch.on = on; g_xch.world = (int)world; g_xch.rank = (int)rank; g_xch.peers = peers; g_xch.scale = (float)scale;
@@ -638,6 +723,13 @@ TORCH_LIBRARY(raw2logit_isp, m) {
     m.def("ssim_backward(Tensor grad, Tensor img1, Tensor img2, int window_size, bool size_average, bool need1, "
           "bool need2) -> (Tensor, Tensor)");
     m.def("ssim(Tensor img1, Tensor img2, int window_size, bool size_average) -> Tensor");
+    // staged mode (track_stages=True): one kernel per stage, csrc/isp_stages.cu; autograd nodes in raw2logit_b200/staged.py
+    m.def("stage_conv(Tensor x, Tensor weight, bool reflect) -> Tensor");
+    m.def("stage_conv_backward(Tensor x, Tensor weight, Tensor grad_y, bool reflect, bool need_x, bool need_w) -> (Tensor, Tensor)");
+    m.def("stage_clip(Tensor x, float lo, float hi) -> Tensor");
+    m.def("stage_clip_backward(Tensor x, Tensor grad_y, float lo, float hi) -> Tensor");
+    m.def("stage_gamma(Tensor x, Tensor gamma) -> Tensor");
+    m.def("stage_gamma_backward(Tensor x, Tensor y, Tensor grad_y, Tensor gamma, bool need_x) -> (Tensor, Tensor)");
     // process-wide state of the fused data-parallel exchange (parallel.enable_fused_gradient_exchange)
     m.def("set_exchange(int world, int rank, int peers, float scale, bool on) -> ()", &set_exchange);
 }
@@ -657,6 +749,12 @@ TORCH_LIBRARY_IMPL(raw2logit_isp, CUDA, m) {
     m.impl("ssim_backward", &ssim_backward_cuda);
     m.impl("ssim", &ssim_forward_cuda);
     m.impl("mosaic_ad", &mosaic_cuda);
+    m.impl("stage_conv", &stage_conv_cuda);
+    m.impl("stage_conv_backward", &stage_conv_backward_cuda);
+    m.impl("stage_clip", &stage_clip_cuda);
+    m.impl("stage_clip_backward", &stage_clip_backward_cuda);
+    m.impl("stage_gamma", &stage_gamma_cuda);
+    m.impl("stage_gamma_backward", &stage_gamma_backward_cuda);
 }
 
 TORCH_LIBRARY_IMPL(raw2logit_isp, Autograd, m) {

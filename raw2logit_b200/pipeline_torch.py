@@ -178,76 +178,12 @@ class ParametrizedProcessing(nn.Module):
         return rgb
 
 
-def _channel_mix(x, m):
-    """y[b,k,h,w] = sum_c x[b,c,h,w] * m[k,c]  (the reference's einsum 'bchw,kc->bkhw')."""
-    return torch.einsum('bchw,kc->bkhw', x, m).contiguous()
-
-
 def _forward_staged(self, raw):
     """``track_stages=True``: every intermediate of the chain is materialised as its own autograd node so that
     ``processor.stages[name]`` and ``processor.stages[name].grad`` exist for ``model.track_images``
-    (reference model.py:204-300, pipeline_torch.py:183-221).
-
-    This is the inspection path, run on a handful of images at epoch ends, not the training hot path: it issues one
-    stock CUDA op per stage (full fp32: TF32 is switched off for its convolutions / matmuls) and
-    includes the reference's YUV->RGB->YUV round trip after sharpening (:197-200), which the fused kernels skip.
-    """
-    import torch.nn.functional as F
-    dev = raw.device
-    bl = self.black_level
-    b, h, w = raw.shape
-    x = raw if raw.dtype == torch.float32 else raw.to(torch.float32)
-    if raw.dtype == torch.uint16:
-        x = raw.to(torch.int32).to(torch.float32) / float(2 ** self.raw_bits - 1)
-    cudnn_tf32, matmul_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    try:
-        mosaic = torch.zeros((b, 3, h, w), device=dev, dtype=torch.float32)
-        mosaic[:, 0, 0::2, 0::2] = x[:, 0::2, 0::2] - bl[0]
-        mosaic[:, 1, 0::2, 1::2] = x[:, 0::2, 1::2] - bl[1]
-        mosaic[:, 1, 1::2, 0::2] = x[:, 1::2, 0::2] - bl[2]
-        mosaic[:, 2, 1::2, 1::2] = x[:, 1::2, 1::2] - bl[3]
-        self.stages['demosaic'] = mosaic
-
-        rgb = F.conv2d(F.pad(mosaic, (1, 1, 1, 1), mode='reflect'), self.debayer.weight)
-        rgb = rgb * self.white_balance.reshape(1, 3, 1, 1)
-        rgb = _channel_mix(rgb, self.colour_correction)
-        self.stages['color_correct'] = rgb
-
-        yuv = _channel_mix(rgb, self.M_RGB_2_YUV)
-        y = F.conv2d(yuv[:, 0:1], self.sharpening_filter.weight, padding=1)
-        yuv = torch.cat([y, yuv[:, 1:]], dim=1)
-        rgb = _channel_mix(yuv, self.M_YUV_2_RGB)
-        self.stages['sharpening'] = rgb
-
-        yuv = _channel_mix(rgb, self.M_RGB_2_YUV)
-        y = F.conv2d(F.pad(yuv[:, 0:1], (2, 2, 2, 2), mode='reflect'), self.gaussian_blur.weight)
-        yuv = torch.cat([y, yuv[:, 1:]], dim=1)
-        rgb = _channel_mix(yuv, self.M_YUV_2_RGB)
-        self.stages['gaussian'] = rgb
-
-        rgb = torch.clip(rgb, 1e-5, 1)
-        self.stages['clipped'] = rgb
-
-        rgb = torch.exp((1 / self.gamma_correct) * torch.log(rgb))
-        self.stages['gamma_correct'] = rgb
-
-        if self.additive_layer is not None:
-            rgb = rgb + self.additive_layer
-            self.stages['noise'] = rgb
-
-        if self.batch_norm is not None:
-            rgb = self.batch_norm(rgb)
-    finally:
-        torch.backends.cudnn.allow_tf32 = cudnn_tf32
-        torch.backends.cuda.matmul.allow_tf32 = matmul_tf32
-
-    if raw.requires_grad:
-        for stage in self.stages.values():
-            stage.retain_grad()
-    self.buffer['processed_rgb'] = rgb
-    return rgb
+    (reference model.py:204-300, pipeline_torch.py:183-221) -- one repo kernel per stage, see ``staged.py``."""
+    from . import staged
+    return staged.forward_staged(self, raw)
 
 
 ParametrizedProcessing._forward_staged = _forward_staged

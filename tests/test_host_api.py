@@ -24,7 +24,7 @@ def test_library_exports_every_symbol_the_header_declares(lib):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.r2l_isp_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.r2l_isp_abi_version() == _lib.ABI_VERSION == 6
     assert b"shape" in lib.r2l_isp_error_string(-1)
     assert lib.r2l_isp_workspace_bytes(64, 256, 256) >= 155 * 4
 
