@@ -60,6 +60,11 @@ def _stub(name, **attrs):
         return
     mod = types.ModuleType(name)
     mod.__dict__.update(attrs)
+    # a stub that shadows one of this repo's own drop-in packages (processing/, utils/) stays a package: later
+    # `import utils.ssim` / `import processing.pipeline_torch` in the same process must still find the real files
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), *name.split("."))
+    if os.path.isdir(here):
+        mod.__path__ = [here]
     sys.modules[name] = mod
 
 

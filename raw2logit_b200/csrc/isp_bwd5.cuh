@@ -39,6 +39,28 @@ template <int TH_, int TW_, int NT_, bool GRAW_, bool TAIL_> struct Bwd5Cfg : Bw
 
 inline bool bwd5_shape_ok(int H, int W) { return bwd4_shape_ok(H, W); }
 
+#ifndef R2L_HOST_EMU
+// Tensor maps of the tensors the backward streams, used ONLY to prefetch the next tile's boxes into the L2
+// (cp.async.bulk.prefetch.tensor: one instruction of one thread per box -- the per-thread prefetch.global.L2 variants cost
+// more issue slots than they saved).  The phases then find their demand loads in the L2 instead of DRAM.
+struct alignas(64) Bwd5Maps {
+    CUtensorMap gout, out;      // (W, H, 3, B) fp32, box (TW + 8, TH + 8, 3, 2)
+    CUtensorMap luma;           // (2 W, H, pairs, 2) fp32, box (2 TW, TH, 1, 2)
+    CUtensorMap raw;            // (W, H, B), box (TW, TH, 2)
+    int on;                     // 0: no prefetch; bits 0-3 = point of the gout / out prefetch, bits 4-7 = of luma / raw
+};
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+#else
+struct Bwd5Maps { int on; };
+#endif
+
 // bit pattern of a float
 R2L_HD unsigned fbits(float x) {
 #ifdef R2L_HOST_EMU
@@ -141,7 +163,7 @@ template <int NT> __device__ __forceinline__ void peer_allreduce(const BwdArgs& 
 #endif
 
 template <class Cfg, typename RawT>
-R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid, float* smem) {
+R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid, float* smem, const Bwd5Maps* maps = nullptr) {
     constexpr int TH = Cfg::TH, TW = Cfg::TW, NT = Cfg::NT, PN = Cfg::PN, G = Cfg::G, HALF = Cfg::HALF;
     constexpr int GG = G + 2;                                     // runs -1 .. G
     Tables2* T2 = reinterpret_cast<Tables2*>(smem);
@@ -193,6 +215,25 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         int b0, b1, ty0, tx0;
         decode_pair_tile(grid, tile, TH, TW, a.B, b0, b1, ty0, tx0);
         const bool dup = b1 == b0;
+#ifndef R2L_HOST_EMU
+        // the next tile's boxes -> L2 (one thread); point 1: tile start, 2: B6 start, 3: B7 start
+        auto prefetch_next = [&](int point) {
+            if (!maps || !maps->on || threadIdx.x != 0 || tile + n_cta >= grid.n) return;
+            const bool big = (maps->on & 15) == point, small = ((maps->on >> 4) & 15) == point;
+            if (!big && !small) return;
+            int nb0, nb1, nty0, ntx0;
+            decode_pair_tile(grid, tile + n_cta, TH, TW, a.B, nb0, nb1, nty0, ntx0);
+            if (big) {
+                tma_prefetch_4d(&maps->gout, ntx0 - 4, nty0 - 4, 0, nb0);
+                tma_prefetch_4d(&maps->out, ntx0 - 4, nty0 - 4, 0, nb0);
+            }
+            if (small) {
+                tma_prefetch_4d(&maps->luma, 2 * ntx0, nty0, nb0 >> 1, 0);
+                tma_prefetch_3d(&maps->raw, ntx0, nty0, nb0);
+            }
+        };
+        prefetch_next(1);
+#endif
         const RawT* imgA = static_cast<const RawT*>(a.raw) + (size_t)b0 * plane;
         const RawT* imgB = static_cast<const RawT*>(a.raw) + (size_t)b1 * plane;
         const float* y0pair = a.luma + (size_t)(b0 >> 1) * plane * 2;   // Y0 of this image pair, [H][W][2]
@@ -514,6 +555,9 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         R2L_SYNC();
 
         // ---- B6: gY0 = corr^T(gY1, Ws) (zero pad) on rows -1..TH, runs -1..G, zero outside the image; Ws statistic ----
+#ifndef R2L_HOST_EMU
+        prefetch_next(2);
+#endif
         { R2L_FOR_THREADS(NT) {
             float ws[9];
 #pragma unroll
@@ -588,6 +632,9 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         } }
         R2L_SYNC();
 
+#ifndef R2L_HOST_EMU
+        prefetch_next(3);
+#endif
         // ---- B7: Q' / P statistics and g_raw from the (gY0, gU, gV) windows; border rules as in isp_bwd3.cuh B7 ----
         // One gradient plane k and one TAP ROW A of the 3x3 at a time over the thread's items (rows of its CFA row phase
         // x runs): only that pass's six packed (image A, image B) Q' sums are live, a tap costs one FFMA2 for the

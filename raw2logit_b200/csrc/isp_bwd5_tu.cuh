@@ -5,9 +5,9 @@
 namespace r2l {
 
 template <class Cfg, typename RawT, int CPS>
-__global__ void __launch_bounds__(Cfg::NT, CPS) isp_backward5_kernel(BwdArgs a, TileGrid grid) {
+__global__ void __launch_bounds__(Cfg::NT, CPS) isp_backward5_kernel(BwdArgs a, TileGrid grid, const __grid_constant__ Bwd5Maps maps) {
     extern __shared__ __align__(128) float smem[];
-    bwd5_cta<Cfg, RawT>(blockIdx.x, gridDim.x, a, grid, smem);
+    bwd5_cta<Cfg, RawT>(blockIdx.x, gridDim.x, a, grid, smem, &maps);
 }
 
 template <class Cfg, typename RawT, int CPS>
@@ -20,9 +20,12 @@ static int launch_backward5_t(const BwdArgs& a, cudaStream_t st, int* grid_used)
     if (g > grid.n) g = grid.n;
     if (g > kMaxCtas) g = kMaxCtas;
     if (rc != R2L_OK) return rc;
+    Bwd5Maps maps;
+    static const int mode = [] { const char* v = getenv("R2L_ISP_BWD_PREFETCH"); return v ? (int)strtol(v, nullptr, 16) : 0; }();
+    maps.on = (mode && make_bwd5_prefetch_maps(&maps, a, sizeof(RawT), Cfg::TH, Cfg::TW)) ? mode : 0;
     BwdArgs a2 = a;
     a2.ticket_gen = next_ticket_generation();                   // no memset in front of the kernel (take_ticket, isp_bwd5.cuh)
-    cudaError_t e = launch_pdl(pdl_enabled_backward(), isp_backward5_kernel<Cfg, RawT, CPS>, g, Cfg::NT, Cfg::kSmemBytes, st, a2, grid);
+    cudaError_t e = launch_pdl(pdl_enabled_backward(), isp_backward5_kernel<Cfg, RawT, CPS>, g, Cfg::NT, Cfg::kSmemBytes, st, a2, grid, maps);
     if (grid_used) *grid_used = g;
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);
 }

@@ -415,6 +415,47 @@ bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_bytes, int 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// generic fp32 / uint16 tiled map: dims / strides (bytes, dims 1..rank-1) / box, zero fill, no swizzle
+static bool encode_map(CUtensorMap* map, const void* base, int elem_bytes, int rank, const cuuint64_t* gdim,
+                       const cuuint64_t* gstride, const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    if (reinterpret_cast<uintptr_t>(base) & 15) return false;
+    for (int i = 0; i + 1 < rank; ++i) if (gstride[i] % 16 != 0) return false;
+    for (int i = 0; i < rank; ++i) if (box[i] == 0 || box[i] > 256) return false;
+    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+    return fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool make_bwd5_prefetch_maps(Bwd5Maps* m, const BwdArgs& a, int raw_elem_bytes, int th, int tw) {
+    if (!a.out || !a.luma) return false;
+    const cuuint64_t W = (cuuint64_t)a.W, H = (cuuint64_t)a.H, B = (cuuint64_t)a.B, P = (B + 1) / 2;
+    {
+        const cuuint64_t gdim[4] = {W, H, 3, B};
+        const cuuint64_t gstr[3] = {W * 4, W * H * 4, W * H * 12};
+        const cuuint32_t box[4] = {(cuuint32_t)tw + 8, (cuuint32_t)th + 8, 3, 2};
+        if (!encode_map(&m->gout, a.gout, 4, 4, gdim, gstr, box)) return false;
+        if (!encode_map(&m->out, a.out, 4, 4, gdim, gstr, box)) return false;
+    }
+    {
+        const cuuint64_t gdim[4] = {2 * W, H, P, 2};
+        const cuuint64_t gstr[3] = {W * 8, W * H * 8, W * H * P * 8};
+        const cuuint32_t box[4] = {(cuuint32_t)(2 * tw), (cuuint32_t)th, 1, 2};
+        if (!encode_map(&m->luma, a.luma, 4, 4, gdim, gstr, box)) return false;
+    }
+    {
+        const cuuint64_t eb = (cuuint64_t)raw_elem_bytes;
+        const cuuint64_t gdim[3] = {W, H, B};
+        const cuuint64_t gstr[2] = {W * eb, W * H * eb};
+        const cuuint32_t box[3] = {(cuuint32_t)tw, (cuuint32_t)th, 2};
+        if (!encode_map(&m->raw, a.raw, raw_elem_bytes, 3, gdim, gstr, box)) return false;
+    }
+    return true;
+}
+
 // the fused finish's ticket counter lives behind the per-CTA statistics rows of the workspace
 constexpr size_t kTicketOffset = (size_t)kMaxCtas * kStatPitch * sizeof(float);
 

@@ -66,6 +66,11 @@ static cudaError_t launch_pdl(bool allow, void (*kernel)(KArgs...), int grid, in
 // false when the shape/pointer does not meet TMA's 16-byte rules (then a non-TMA kernel runs)
 bool make_raw_tensor_map(CUtensorMap* map, const void* raw, int elem_bytes, int B, int H, int W, int box_w, int box_h);
 
+// tensor maps for the fifth-generation backward's L2 prefetch of the next tile (isp_bwd5.cuh); false: no prefetch
+struct Bwd5Maps;
+struct BwdArgs;
+bool make_bwd5_prefetch_maps(Bwd5Maps* maps, const BwdArgs& a, int raw_elem_bytes, int th, int tw);
+
 // launchers, one translation unit each (compiled in parallel by _build.py)
 // *fused_tail (may be null): the launch ran the fused train-mode BatchNorm tail itself (FwdArgs::bn_sync, third generation)
 int launch_forward_f32(const FwdArgs& a, bool stats, cudaStream_t st, int* grid_used, bool* fused_tail = nullptr);
