@@ -512,6 +512,9 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     st4<PN>(GY1, (ir[u] + 2) * PN + 2 * (ig[u] + 2), out[u][0], out[u][1], out[u][2], out[u][3]);
                 }
             }
+#ifndef R2L_HOST_EMU
+            load_c6(tid, c6);          // B6's Y0 centres, ahead of the halo ring (in-call A/B: -1.5 us against after it)
+#endif
             // -- halo ring: single runs, no statistic
             for (int item = TH * G + tid; item < Cfg::G1H * GG; item += NT) {
                 int r, g;
@@ -548,9 +551,6 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 }
                 st4<PN>(GY1, (r + 2) * PN + 2 * (g + 2), out[0], out[1], out[2], out[3]);
             }
-#ifndef R2L_HOST_EMU
-            load_c6(tid, c6);
-#endif
         } }
         R2L_SYNC();
 

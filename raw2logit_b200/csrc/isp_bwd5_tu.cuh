@@ -21,7 +21,9 @@ static int launch_backward5_t(const BwdArgs& a, cudaStream_t st, int* grid_used)
     if (g > kMaxCtas) g = kMaxCtas;
     if (rc != R2L_OK) return rc;
     Bwd5Maps maps;
-    static const int mode = [] { const char* v = getenv("R2L_ISP_BWD_PREFETCH"); return v ? (int)strtol(v, nullptr, 16) : 0; }();
+    // default 0x33: both groups of boxes at the start of B7 (in-call A/B, profiles/r02_experiments.md: 89.3 us without,
+    // 87.3 us with; at the start of the tile -- 23 us ahead -- the boxes are evicted again before use: 93.8 us)
+    static const int mode = [] { const char* v = getenv("R2L_ISP_BWD_PREFETCH"); return v ? (int)strtol(v, nullptr, 16) : 0x33; }();
     maps.on = (mode && make_bwd5_prefetch_maps(&maps, a, sizeof(RawT), Cfg::TH, Cfg::TW)) ? mode : 0;
     BwdArgs a2 = a;
     a2.ticket_gen = next_ticket_generation();                   // no memset in front of the kernel (take_ticket, isp_bwd5.cuh)
