@@ -103,8 +103,11 @@ class PeerExchange:
 def enable_fused_gradient_exchange(group=None, average=True):
     """From now on the ISP's fused backward (module API: ``ParametrizedProcessing`` under autograd) returns parameter
     gradients that are already summed (``average=False``) or averaged over the ranks of ``group``: the exchange runs
-    inside the backward kernel (``PeerExchange``).  All-reduce only the *other* parameters afterwards, e.g.
-    ``allreduce_gradients(task_model.parameters())``.  Every rank must run the same sequence of ISP backward calls.
+    inside the backward kernel (``PeerExchange``).  Only the 132 in-kernel gradients are exchanged: all-reduce every
+    *other* parameter afterwards -- the task model's and, in adversarial mode, ``processor.additive_layer`` (its gradient
+    is a separate batch sum and stays rank-local), e.g. ``allreduce_gradients([*task_model.parameters(),
+    processor.additive_layer])``.  The staged path (``track_stages=True``) does not take part in the exchange and warns
+    when it runs while the exchange is enabled.  Every rank must run the same sequence of ISP backward calls.
     Returns the ``PeerExchange``; ``disable_fused_gradient_exchange()`` restores local gradients."""
     from . import ops
     exchange = PeerExchange(group)

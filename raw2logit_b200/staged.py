@@ -91,6 +91,10 @@ def luma_stage_weight(luma_taps, rgb2yuv, yuv2rgb):
 
 def forward_staged(self, raw):
     """``ParametrizedProcessing.forward`` for ``track_stages=True`` (bound as ``_forward_staged``)."""
+    if ops._exchange is not None:
+        import warnings
+        warnings.warn("track_stages=True runs the stage kernels: its parameter gradients are rank-local, the fused "
+                      "data-parallel gradient exchange does not apply to this call", RuntimeWarning, stacklevel=3)
     self.stages['demosaic'] = rgb = ops.mosaic(raw, self.black_level, reduce_size=False, out_channels=3,
                                                raw_denominator=float(2 ** self.raw_bits - 1))
 
