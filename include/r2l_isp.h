@@ -109,15 +109,20 @@ size_t r2l_isp_workspace_bytes(int B, int H, int W);
  * always enables it): forward kernel that also reduces per-channel sum / sum of squares, a finish kernel that
  * forms batch mean / biased variance, writes saved_affine = {1/sqrt(var+eps)[3], -mean/sqrt(var+eps)[3]} and
  * updates running_mean / running_var in place like torch (momentum, unbiased variance; either may be NULL), and
- * an in-place normalisation of out.  additive may be NULL. */
+ * an in-place normalisation of out.  additive may be NULL.  num_batches_tracked (may be NULL): one int64 on the
+ * device, incremented by one (nn.BatchNorm2d's counter; in the kernel, so a captured launch counts its replays). */
 int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
                              const r2l_isp_params* params, const float* additive, float* out,
-                             float* running_mean, float* running_var, float momentum, float eps,
-                             float* saved_affine, float* saved_luma, void* workspace, size_t workspace_bytes,
+                             float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                             float eps, float* saved_affine, float* saved_luma, void* workspace, size_t workspace_bytes,
                              void* stream);
 
 /* Backward of that tail, part 1: reduces sum(grad_out), sum(grad_out * out) per channel and writes the 15-float
- * grad_tail {gs[3], c1[3], c2[3], ysc[3], ysh[3]} that r2l_isp_backward consumes. */
+ * grad_tail {gs[3], c1[3], c2[3], ysc[3], ysh[3]} that r2l_isp_backward consumes.
+ * With the full workspace (r2l_isp_workspace_bytes) the tail is DEFERRED: the per-CTA sums stay in the workspace, c1 / c2
+ * of grad_tail carry a tag, and the next r2l_isp_backward / r2l_isp_backward_dp call on the same stream WITH THE SAME
+ * WORKSPACE finishes them inside its kernel (no separate finish launch); treat grad_tail as opaque between the two
+ * calls.  With a smaller workspace (>= 3 * 296 * 2 floats) grad_tail is complete when this call's work is done. */
 int r2l_isp_bn_backward_prepare(const float* grad_out, const float* out, const float* saved_affine, int B, int H,
                                 int W, float* grad_tail, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -72,7 +72,7 @@ def load():
     lib.r2l_isp_workspace_bytes.restype = sz
     lib.r2l_isp_workspace_bytes.argtypes = [ci, ci, ci]
     lib.r2l_isp_forward_bn_train.restype = ci
-    lib.r2l_isp_forward_bn_train.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(IspParams), vp, vp, vp, vp, cf, cf,
+    lib.r2l_isp_forward_bn_train.argtypes = [vp, ci, cf, ci, ci, ci, ctypes.POINTER(IspParams), vp, vp, vp, vp, vp, cf, cf,
                                              vp, vp, vp, sz, vp]
     lib.r2l_isp_bn_backward_prepare.restype = ci
     lib.r2l_isp_bn_backward_prepare.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, sz, vp]

@@ -210,6 +210,48 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
     // library's kernels), shared and tensor memory.  The forward output, the luma planes and grad_out are read -- and the
     // workspace, grad_raw, the gradients written -- after the wait.  A no-op for a plain launch.
     pdl_wait();
+    // The BatchNorm / additive tail, once per CTA: {gs, c1, c2, 1/ysc, -ysh/ysc} per channel in shared memory.  A deferred
+    // tail (kTailDeferredTag in c1) is finished here from the statistics kernel's per-CTA sums -- one warp per channel,
+    // lanes stride over the rows, fp64, xor tree: the arithmetic and order of bn_backward_finish_kernel, the same in
+    // every CTA -- instead of by a one-CTA launch between the two kernels (5 us per step).
+    __shared__ float s_tail[15];
+    if (Cfg::TAIL) {
+        const int c = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+        if (c < 3) {
+            float c1 = a.gtail[3 + c], c2 = a.gtail[6 + c];
+            if (a.bn_partials && fbits(a.gtail[3]) == kTailDeferredTag) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int i = lane; i < kBnBwdBlocks; i += 32) {
+                    s1 += (double)__ldcg(a.bn_partials + ((size_t)c * kBnBwdBlocks + i) * 2);
+                    s2 += (double)__ldcg(a.bn_partials + ((size_t)c * kBnBwdBlocks + i) * 2 + 1);
+                }
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                c1 = (float)(s1 / a.bn_count);
+                c2 = (float)(s2 / a.bn_count);
+            }
+            if (lane == 0) {
+                const float isc = 1.0f / a.gtail[9 + c];
+                s_tail[c] = a.gtail[c]; s_tail[3 + c] = c1; s_tail[6 + c] = c2;
+                s_tail[9 + c] = isc; s_tail[12 + c] = -a.gtail[12 + c] * isc;
+            }
+        }
+        __syncthreads();
+    }
+    const float* tail = s_tail;
+#else
+    float tail_emu[15] = {0.f};
+    if (Cfg::TAIL) {
+        for (int c = 0; c < 3; ++c) {
+            const float isc = 1.0f / a.gtail[9 + c];
+            tail_emu[c] = a.gtail[c]; tail_emu[3 + c] = a.gtail[3 + c]; tail_emu[6 + c] = a.gtail[6 + c];
+            tail_emu[9 + c] = isc; tail_emu[12 + c] = -a.gtail[12 + c] * isc;
+        }
+    }
+    const float* tail = tail_emu;
 #endif
     for (int tile = cta; tile < grid.n; tile += n_cta) {
         int b0, b1, ty0, tx0;
@@ -343,8 +385,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                         const float adk[4] = {ad[k].x, ad[k].y, ad[k].z, ad[k].w};
                         float t_gs = 1.f, t_c1 = 0.f, t_c2 = 0.f, t_isc = 1.f, t_osh = 0.f;
                         if (Cfg::TAIL) {
-                            t_gs = a.gtail[k]; t_c1 = a.gtail[3 + k]; t_c2 = a.gtail[6 + k];
-                            t_isc = 1.0f / a.gtail[9 + k]; t_osh = -a.gtail[12 + k] * t_isc;
+                            t_gs = tail[k]; t_c1 = tail[3 + k]; t_c2 = tail[6 + k]; t_isc = tail[9 + k]; t_osh = tail[12 + k];
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {

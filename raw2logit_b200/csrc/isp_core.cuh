@@ -326,6 +326,7 @@ struct FwdArgs {
     float bn_momentum = 0.f, bn_eps = 0.f;
     float* bn_running_mean = nullptr;      // may be null
     float* bn_running_var = nullptr;       // may be null
+    long long* bn_num_batches = nullptr;   // may be null: nn.BatchNorm2d.num_batches_tracked, incremented by CTA 0
     float* bn_saved_affine = nullptr;      // {1/sqrt(var+eps)[3], -mean/sqrt(var+eps)[3]}
 };
 constexpr int kChanPitch = 8;
@@ -467,6 +468,9 @@ template <int TH_, int TW_, int NT_, bool GRAW_> struct BwdCfg {
     static_assert(NT_ % TW_ == 0 && ((NT_ / TW_) % 2) == 0 && TW_ % 32 == 0 && TH_ % 2 == 0, "phase-stable mapping");
 };
 
+constexpr int kBnBwdBlocks = 296;                  // CTAs per channel of the BatchNorm backward statistics kernel
+constexpr unsigned kTailDeferredTag = 0x7fc0b200u; // quiet NaN with a payload no arithmetic produces
+
 struct BwdArgs {
     const void* raw; float denom; int B, H, W;
     Params P;
@@ -474,6 +478,12 @@ struct BwdArgs {
     const float* gtail;    // null or 15 floats {gs[3], c1[3], c2[3], ysc[3], ysh[3]}: the BatchNorm tail's backward,
                            // dL/do = gs*(G - c1 - c2*yhat) with yhat = (o + additive)*ysc + ysh (eval mode: c1=c2=0)
     const float* additive; // (3,H,W) or null, only read when gtail is given
+    // Deferred tail (r2l_isp_bn_backward_prepare with the full workspace): gtail's c1 / c2 entries carry kTailDeferredTag
+    // and the per-CTA sums of the statistics kernel are still in the workspace; the fifth-generation kernel finishes
+    // them in its prologue (no separate finish launch), older generations get a resolved copy (tail_ws) from the host.
+    const float* bn_partials = nullptr;    // [3][kBnBwdBlocks][2]: sum(gy), sum(gy * yhat) per statistics CTA
+    double bn_count = 0.0;                 // B * H * W
+    float* tail_ws = nullptr;              // 15 floats of workspace for the resolved copy
     float* graw;           // (B,H,W) or null
     float* partials;       // [n_cta][kStatPitch]
     const float* out;      // null, or the forward's output (B,3,H,W): lets the vectorised backward skip the Gaussian /

@@ -450,6 +450,7 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
                         a.bn_saved_affine[c] = (float)inv;
                         a.bn_saved_affine[3 + c] = (float)(-mean * inv);
                         const double m = (double)a.bn_momentum;
+                        if (c == 0 && a.bn_num_batches) *a.bn_num_batches += 1;      // nn.BatchNorm2d bookkeeping
                         if (a.bn_running_mean) a.bn_running_mean[c] = (float)((1.0 - m) * (double)a.bn_running_mean[c] + m * mean);
                         if (a.bn_running_var) {
                             const double unbiased = a.bn_count > 1.0 ? var * a.bn_count / (a.bn_count - 1.0) : var;

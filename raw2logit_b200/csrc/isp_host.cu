@@ -20,7 +20,7 @@ namespace r2l {
 // per-CTA channel sums -> batch mean / biased variance -> {scale, shift}; running statistics updated in place
 // exactly like torch (momentum update, unbiased variance for the running estimate).
 __global__ void bn_finish_kernel(const float* partials, int n_cta, double count, float momentum, float eps,
-                                 float* running_mean, float* running_var, float* affine) {
+                                 float* running_mean, float* running_var, float* affine, long long* num_batches) {
     // one warp per channel; lanes stride over the per-CTA partial sums (independent loads), fixed-order fp64 reduction
     const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (c >= 3) return;
@@ -41,6 +41,7 @@ __global__ void bn_finish_kernel(const float* partials, int n_cta, double count,
     const double inv = 1.0 / sqrt(var + (double)eps);
     affine[c] = (float)inv;
     affine[3 + c] = (float)(-mean * inv);
+    if (c == 0 && num_batches) *num_batches += 1;
     if (running_mean) running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
     if (running_var) {
         const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
@@ -72,10 +73,12 @@ __global__ void affine_inplace_kernel(float* x, const float* affine, int BC, int
 // A pure streaming reduction over 24 B/px: 128-bit loads, four independent accumulator pairs per thread (eight loads in
 // flight), two CTAs per SM and channel.  (The first version -- scalar loads into one dependent accumulator chain, 128
 // CTAs per channel -- ran at 1.4 TB/s: 69.6 us for 64 x 256 x 256, more than the fused forward kernel.)
-constexpr int kBnBwdBlocks = 296;
+// head (may be null): deferred mode -- CTA 0 of every channel also writes the channel's entries of the 15-float tail that
+// need no reduction (gs, ysc, ysh from the forward's saved affine) and tags c1 / c2 as "finish me from the partials"
 template <bool VEC>
 __global__ void __launch_bounds__(256) bn_backward_stats_kernel(const float* __restrict__ gy, const float* __restrict__ y,
-                                                                int B, int HW, float* partials /* [3][kBnBwdBlocks][2] */) {
+                                                                int B, int HW, float* partials /* [3][kBnBwdBlocks][2] */,
+                                                                const float* affine, float* head) {
     const int c = blockIdx.y;
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     if (VEC) {                                          // HW % 4 == 0, 16-byte aligned tensors, B * HW / 4 < 2^31
@@ -125,6 +128,36 @@ __global__ void __launch_bounds__(256) bn_backward_stats_kernel(const float* __r
         for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
         partials[((size_t)c * kBnBwdBlocks + blockIdx.x) * 2 + threadIdx.x] = t;
     }
+    if (head && blockIdx.x == 0 && threadIdx.x == 0) {
+        head[c] = affine[c];                                    // gs  = 1/sqrt(var+eps)
+        head[3 + c] = __uint_as_float(kTailDeferredTag);        // c1, c2: from the partials, by the consumer
+        head[6 + c] = __uint_as_float(kTailDeferredTag);
+        head[9 + c] = affine[c];                                // ysc
+        head[12 + c] = affine[3 + c];                           // ysh
+    }
+}
+// one CTA of >= 96 threads: gtail_in (deferred or complete) -> a complete 15-float tail in `out` (for the kernels that
+// do not finish a deferred tail themselves: third generation, generic)
+__global__ void bn_tail_resolve_kernel(const float* gtail_in, const float* partials, double count, float* out) {
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c >= 3) return;
+    float c1 = gtail_in[3 + c], c2 = gtail_in[6 + c];
+    if (partials && __float_as_uint(gtail_in[3]) == kTailDeferredTag) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = lane; i < kBnBwdBlocks; i += 32) {
+            s1 += (double)partials[((size_t)c * kBnBwdBlocks + i) * 2];
+            s2 += (double)partials[((size_t)c * kBnBwdBlocks + i) * 2 + 1];
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        c1 = (float)(s1 / count);
+        c2 = (float)(s2 / count);
+    }
+    if (lane != 0) return;
+    out[c] = gtail_in[c]; out[3 + c] = c1; out[6 + c] = c2; out[9 + c] = gtail_in[9 + c]; out[12 + c] = gtail_in[12 + c];
 }
 __global__ void bn_backward_finish_kernel(const float* partials, const float* affine, double count, float* gtail) {
     const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -458,6 +491,11 @@ bool make_bwd5_prefetch_maps(Bwd5Maps* m, const BwdArgs& a, int raw_elem_bytes, 
 
 // the fused finish's ticket counter lives behind the per-CTA statistics rows of the workspace
 constexpr size_t kTicketOffset = (size_t)kMaxCtas * kStatPitch * sizeof(float);
+// behind the 256 bytes of ticket words: the BatchNorm backward's per-CTA sums (deferred tail) and a resolved tail
+constexpr size_t kBnPartialsOffset = kTicketOffset + 256;
+constexpr size_t kBnPartialsBytes = ((size_t)3 * kBnBwdBlocks * 2 * sizeof(float) + 127) / 128 * 128;
+constexpr size_t kBnTailOffset = kBnPartialsOffset + kBnPartialsBytes;
+constexpr size_t kWorkspaceBytes = kBnTailOffset + 64;
 
 // does a forward call with these arguments run the kernel that can save the luma planes?  (one rule, used by
 // r2l_isp_forward, r2l_isp_forward_bn_train and r2l_isp_luma_supported)
@@ -517,11 +555,20 @@ static int launch_backward_any(const BwdArgs& a, int raw_dtype, float* grads, cu
             if (rc == R2L_OK) return rc;
         }
         if (a.world > 1) return rc == kNotServed ? (int)R2L_ERR_BAD_ARGUMENT : rc;   // the exchange lives in that kernel only
-        if (rc == kNotServed) rc = raw_dtype == R2L_F32 ? launch_backward3_f32(a, st, &g) : launch_backward3_u16(a, st, &g);
     }
-    if (rc == kNotServed) rc = launch_backward_generic(a, raw_dtype, st, &g);
+    // the older generations read a complete tail: resolve a (possibly) deferred one into the workspace first
+    BwdArgs b = a;
+    if (rc == kNotServed && a.gtail && a.tail_ws) {
+        bn_tail_resolve_kernel<<<1, 96, 0, st>>>(a.gtail, a.bn_partials, a.bn_count, a.tail_ws);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e);
+        b.gtail = a.tail_ws;
+    }
+    if (rc == kNotServed && !(force && force[0] == '1'))
+        rc = raw_dtype == R2L_F32 ? launch_backward3_f32(b, st, &g) : launch_backward3_u16(b, st, &g);
+    if (rc == kNotServed) rc = launch_backward_generic(b, raw_dtype, st, &g);
     if (rc != R2L_OK) return rc;
-    return launch_finish(a, g, grads, st);
+    return launch_finish(b, g, grads, st);
 }
 
 }  // namespace r2l
@@ -570,7 +617,7 @@ int r2l_isp_forward(const void* raw, int raw_dtype, float raw_denominator, int B
 
 size_t r2l_isp_workspace_bytes(int B, int H, int W) {
     (void)B; (void)H; (void)W;
-    return kTicketOffset + 256;
+    return kWorkspaceBytes;
 }
 
 size_t r2l_isp_saved_luma_floats(int B, int H, int W) {
@@ -585,8 +632,8 @@ int r2l_isp_luma_supported(const void* raw, int raw_dtype, int B, int H, int W, 
 
 int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominator, int B, int H, int W,
                              const r2l_isp_params* params, const float* additive, float* out,
-                             float* running_mean, float* running_var, float momentum, float eps,
-                             float* saved_affine, float* saved_luma, void* workspace, size_t workspace_bytes,
+                             float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                             float eps, float* saved_affine, float* saved_luma, void* workspace, size_t workspace_bytes,
                              void* stream) {
     int rc = check_common(raw, raw_dtype, B, H, W, params);
     if (rc != R2L_OK) return rc;
@@ -609,6 +656,7 @@ int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominat
         a.bn_gen = next_ticket_generation();
         a.bn_count = (double)B * H * W; a.bn_momentum = momentum; a.bn_eps = eps;
         a.bn_running_mean = running_mean; a.bn_running_var = running_var; a.bn_saved_affine = saved_affine;
+        a.bn_num_batches = num_batches_tracked;
     }
     int g = 0;
     bool fused = false;
@@ -616,7 +664,7 @@ int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominat
     if (rc != R2L_OK) return rc;
     if (fused) return R2L_OK;
     bn_finish_kernel<<<1, 96, 0, st>>>(a.chan_partials, g, (double)B * H * W, momentum, eps, running_mean,
-                                       running_var, saved_affine);
+                                       running_var, saved_affine, num_batches_tracked);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
     const int hw = H * W;
@@ -632,13 +680,20 @@ int r2l_isp_bn_backward_prepare(const float* grad_out, const float* out, const f
     if (!grad_out || !out || !saved_affine || !grad_tail || !workspace) return R2L_ERR_NULL_POINTER;
     if (workspace_bytes < (size_t)3 * kBnBwdBlocks * 2 * sizeof(float)) return R2L_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    float* partials = static_cast<float*>(workspace);
+    // With the full workspace the tail is DEFERRED: the statistics kernel leaves its per-CTA sums in the workspace and tags
+    // c1 / c2 of grad_tail; r2l_isp_backward (same workspace, same stream, next) finishes them in its kernel's prologue.
+    // A caller with the minimal workspace gets the separate one-CTA finish kernel and a complete grad_tail.
+    const bool deferred = workspace_bytes >= kWorkspaceBytes && aligned(workspace, 8);
+    float* partials = deferred ? reinterpret_cast<float*>(static_cast<char*>(workspace) + kBnPartialsOffset)
+                               : static_cast<float*>(workspace);
+    float* head = deferred ? grad_tail : nullptr;
     if (((H * W) & 3) == 0 && aligned(grad_out, 16) && aligned(out, 16) && (size_t)B * H * W / 4 < ((size_t)1 << 31) - 1024)
-        bn_backward_stats_kernel<true><<<dim3(kBnBwdBlocks, 3), 256, 0, st>>>(grad_out, out, B, H * W, partials);
+        bn_backward_stats_kernel<true><<<dim3(kBnBwdBlocks, 3), 256, 0, st>>>(grad_out, out, B, H * W, partials, saved_affine, head);
     else
-        bn_backward_stats_kernel<false><<<dim3(kBnBwdBlocks, 3), 256, 0, st>>>(grad_out, out, B, H * W, partials);
+        bn_backward_stats_kernel<false><<<dim3(kBnBwdBlocks, 3), 256, 0, st>>>(grad_out, out, B, H * W, partials, saved_affine, head);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
+    if (deferred) return R2L_OK;
     bn_backward_finish_kernel<<<1, 96, 0, st>>>(partials, saved_affine, (double)B * H * W, grad_tail);
     e = cudaGetLastError();
     return e == cudaSuccess ? R2L_OK : cuda_fail(e);
@@ -698,6 +753,11 @@ static int backward_impl(const void* raw, int raw_dtype, float raw_denominator, 
     a.gout = grad_out; a.gtail = grad_tail; a.additive = additive; a.graw = grad_raw; a.partials = static_cast<float*>(workspace);
     a.out = out;
     a.luma = out ? saved_luma : nullptr;
+    if (grad_tail) {                                            // a deferred tail is finished from the workspace
+        a.bn_partials = reinterpret_cast<const float*>(static_cast<const char*>(workspace) + kBnPartialsOffset);
+        a.bn_count = (double)B * H * W;
+        a.tail_ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + kBnTailOffset);
+    }
     if (out && additive && !grad_tail) return R2L_ERR_BAD_ARGUMENT;   // an additive tail needs grad_tail to invert it
     if (dp && dp->world > 1) {
         a.peers = dp->peers; a.world = dp->world; a.rank = dp->rank; a.epoch = dp->epoch; a.dp_scale = dp->scale;

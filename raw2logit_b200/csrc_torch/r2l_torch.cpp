@@ -144,8 +144,8 @@ std::tuple<Tensor, Tensor> forward_cuda(const Tensor& raw_, const Tensor& bl, co
 std::tuple<Tensor, Tensor, Tensor> forward_bn_train_cuda(
     const Tensor& raw_, const Tensor& bl, const Tensor& wb, const Tensor& ccm, const Tensor& gamma, const Tensor& wd,
     const Tensor& ws, const Tensor& wg, const Tensor& m1, const Tensor& m2, const optional<Tensor>& additive,
-    const optional<Tensor>& running_mean, const optional<Tensor>& running_var, double momentum, double eps,
-    double raw_denominator, bool save_luma) {
+    const optional<Tensor>& running_mean, const optional<Tensor>& running_var, const optional<Tensor>& num_batches_tracked,
+    double momentum, double eps, double raw_denominator, bool save_luma) {
     int b, h, w, code;
     check_shape(raw_, b, h, w);
     TORCH_CHECK_VALUE((int64_t)b * h * w >= 2, "Expected more than 1 value per channel when training");
@@ -165,13 +165,19 @@ std::tuple<Tensor, Tensor, Tensor> forward_bn_train_cuda(
     };
     rm = stat_ptr(running_mean, "running_mean");
     rv = stat_ptr(running_var, "running_var");
+    long long* nbt = nullptr;
+    if (num_batches_tracked.has_value() && num_batches_tracked->defined()) {
+        TORCH_CHECK_TYPE(num_batches_tracked->scalar_type() == at::kLong && num_batches_tracked->numel() == 1 &&
+                         num_batches_tracked->is_cuda(), "num_batches_tracked must be one int64 on the device");
+        nbt = reinterpret_cast<long long*>(num_batches_tracked->data_ptr<int64_t>());
+    }
     Tensor out = at::empty({b, 3, h, w}, raw.options().dtype(at::kFloat));
     Tensor saved = at::empty({6}, out.options());
     size_t nbytes;
     Tensor wsb = workspace(out, b, h, w, nbytes);
     Tensor luma = luma_buffer(raw, code, b, h, w, out, add.defined() ? add.data_ptr<float>() : nullptr, save_luma);
     check_rc(r2l_isp_forward_bn_train(raw.data_ptr(), code, (float)raw_denominator, b, h, w, &pk.p,
-                                      add.defined() ? add.data_ptr<float>() : nullptr, out.data_ptr<float>(), rm, rv,
+                                      add.defined() ? add.data_ptr<float>() : nullptr, out.data_ptr<float>(), rm, rv, nbt,
                                       (float)momentum, (float)eps, saved.data_ptr<float>(),
                                       luma.numel() ? luma.data_ptr<float>() : nullptr, wsb.data_ptr(), nbytes,
                                       cur_stream(raw)),
@@ -179,7 +185,9 @@ std::tuple<Tensor, Tensor, Tensor> forward_bn_train_cuda(
     return {out, saved, luma};
 }
 
-Tensor bn_backward_prepare_cuda(const Tensor& grad_out, const Tensor& out, const Tensor& saved_affine) {
+// complete = false: with the full workspace the C ABI defers c1 / c2 of the tail to the backward kernel's prologue (no
+// finish launch); complete = true asks for the finished 15 floats (the additive layer's gradient reads them on this side)
+Tensor bn_backward_prepare_cuda(const Tensor& grad_out, const Tensor& out, const Tensor& saved_affine, bool complete) {
     TORCH_CHECK(out.dim() == 4, "out must be (B, 3, H, W)");
     const int b = (int)out.size(0), h = (int)out.size(2), w = (int)out.size(3);
     c10::cuda::CUDAGuard guard(out.device());
@@ -188,6 +196,8 @@ Tensor bn_backward_prepare_cuda(const Tensor& grad_out, const Tensor& out, const
     Tensor tail = at::empty({15}, y.options());
     size_t nbytes;
     Tensor wsb = workspace(y, b, h, w, nbytes);
+    if (complete || env_is("R2L_ISP_BN_TAIL_COMPLETE", '1'))                   // (the variable: debugging knob, tests compare the two)
+        nbytes = (size_t)3 * 296 * 2 * sizeof(float);                          // the minimal workspace: separate finish kernel
     check_rc(r2l_isp_bn_backward_prepare(g.data_ptr<float>(), y.data_ptr<float>(), sa.data_ptr<float>(), b, h, w,
                                          tail.data_ptr<float>(), wsb.data_ptr(), nbytes, cur_stream(y)),
              "r2l_isp_bn_backward_prepare");
@@ -530,8 +540,8 @@ struct FusedISPFn : public torch::autograd::Function<FusedISPFn> {
     static Tensor forward(torch::autograd::AutogradContext* ctx, const Tensor& raw, const Tensor& bl, const Tensor& wb,
                           const Tensor& ccm, const Tensor& gamma, const Tensor& wd, const Tensor& ws, const Tensor& wg,
                           const Tensor& m1, const Tensor& m2, const optional<Tensor>& additive, int64_t bn_mode,
-                          const optional<Tensor>& running_mean, const optional<Tensor>& running_var, double momentum,
-                          double eps, double raw_denominator) {
+                          const optional<Tensor>& running_mean, const optional<Tensor>& running_var,
+                          const optional<Tensor>& num_batches_tracked, double momentum, double eps, double raw_denominator) {
         at::AutoDispatchBelowADInplaceOrView guard;
         const Tensor* const ps[7] = {&bl, &wb, &ccm, &gamma, &wd, &ws, &wg};
         bool any_param = false;
@@ -543,7 +553,7 @@ struct FusedISPFn : public torch::autograd::Function<FusedISPFn> {
         Tensor out, luma, saved_affine;
         if (bn_mode == 2) {
             auto r = op_forward_bn().call(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, running_mean, running_var,
-                                          momentum, eps, raw_denominator, save_luma);
+                                          num_batches_tracked, momentum, eps, raw_denominator, save_luma);
             out = std::get<0>(r); saved_affine = std::get<1>(r); luma = std::get<2>(r);
         } else {
             optional<Tensor> aff;
@@ -582,11 +592,11 @@ struct FusedISPFn : public torch::autograd::Function<FusedISPFn> {
         const int64_t np = ctx->saved_data["need_params"].toInt();
         const bool any_param = np != 0;
         Tensor grad_out = grad_outputs[0].contiguous();
-        torch::autograd::variable_list grads(17);
+        torch::autograd::variable_list grads(18);
         // 15-float description of the tail the forward applied: {gs, c1, c2, ysc, ysh} x 3 channels (r2l_isp.h)
         Tensor tail;
         if (bn_mode == 2) {
-            tail = op_bn_prepare().call(grad_out, out_saved, saved_affine);
+            tail = op_bn_prepare().call(grad_out, out_saved, saved_affine, additive.defined() && need_add);
         } else if (bn_mode == 1) {
             Tensor zeros = at::zeros({6}, saved_affine.options());
             tail = at::cat({saved_affine.narrow(0, 0, 3), zeros, saved_affine});    // gs = ysc = scale, c1 = c2 = 0, ysh = shift
@@ -627,19 +637,21 @@ struct FusedISPFn : public torch::autograd::Function<FusedISPFn> {
 Tensor fused_autograd(const Tensor& raw, const Tensor& bl, const Tensor& wb, const Tensor& ccm, const Tensor& gamma,
                       const Tensor& wd, const Tensor& ws, const Tensor& wg, const Tensor& m1, const Tensor& m2,
                       const optional<Tensor>& additive, int64_t bn_mode, const optional<Tensor>& running_mean,
-                      const optional<Tensor>& running_var, double momentum, double eps, double raw_denominator) {
+                      const optional<Tensor>& running_var, const optional<Tensor>& num_batches_tracked, double momentum,
+                      double eps, double raw_denominator) {
     return FusedISPFn::apply(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, bn_mode, running_mean, running_var,
-                             momentum, eps, raw_denominator);
+                             num_batches_tracked, momentum, eps, raw_denominator);
 }
 
 // the same forward without a graph: torch.inference_mode() skips the Autograd key
 Tensor fused_cuda(const Tensor& raw, const Tensor& bl, const Tensor& wb, const Tensor& ccm, const Tensor& gamma,
                   const Tensor& wd, const Tensor& ws, const Tensor& wg, const Tensor& m1, const Tensor& m2,
                   const optional<Tensor>& additive, int64_t bn_mode, const optional<Tensor>& running_mean,
-                  const optional<Tensor>& running_var, double momentum, double eps, double raw_denominator) {
+                  const optional<Tensor>& running_var, const optional<Tensor>& num_batches_tracked, double momentum,
+                  double eps, double raw_denominator) {
     if (bn_mode == 2)
         return std::get<0>(forward_bn_train_cuda(raw, bl, wb, ccm, gamma, wd, ws, wg, m1, m2, additive, running_mean,
-                                                 running_var, momentum, eps, raw_denominator, false));
+                                                 running_var, num_batches_tracked, momentum, eps, raw_denominator, false));
     optional<Tensor> aff;
     if (bn_mode == 1) {
         TORCH_CHECK(running_mean.has_value() && running_var.has_value(), "eval-mode BatchNorm needs running statistics");
@@ -703,9 +715,10 @@ TORCH_LIBRARY(raw2logit_isp, m) {
     m.def("forward(Tensor raw, " R2L_PARAMS_SCHEMA ", Tensor? additive, Tensor? affine, float raw_denominator, "
           "bool save_luma=False) -> (Tensor, Tensor)");
     m.def("forward_bn_train(Tensor raw, " R2L_PARAMS_SCHEMA ", Tensor? additive, Tensor(a!)? running_mean, "
-          "Tensor(b!)? running_var, float momentum, float eps, float raw_denominator, bool save_luma=False) "
+          "Tensor(b!)? running_var, Tensor(c!)? num_batches_tracked, float momentum, float eps, float raw_denominator, "
+          "bool save_luma=False) "
           "-> (Tensor, Tensor, Tensor)");
-    m.def("bn_backward_prepare(Tensor grad_out, Tensor out, Tensor saved_affine) -> Tensor");
+    m.def("bn_backward_prepare(Tensor grad_out, Tensor out, Tensor saved_affine, bool complete=False) -> Tensor");
     m.def("backward(Tensor raw, " R2L_PARAMS_SCHEMA ", Tensor grad_out, Tensor? grad_tail, Tensor? additive, "
           "Tensor? out, Tensor? luma, bool need_raw_grad, float raw_denominator) -> (Tensor, Tensor)");
     m.def("mosaic(Tensor raw, Tensor? black_level, bool reduce_size, int out_channels, float raw_denominator) -> Tensor");
@@ -713,7 +726,7 @@ TORCH_LIBRARY(raw2logit_isp, m) {
     m.def("batch_sum(Tensor x, Tensor? scale) -> Tensor");
     // differentiable entry points (C++ autograd nodes)
     m.def("fused(Tensor raw, " R2L_PARAMS_SCHEMA ", Tensor? additive, int bn_mode, Tensor(a!)? running_mean, "
-          "Tensor(b!)? running_var, float momentum, float eps, float raw_denominator) -> Tensor");
+          "Tensor(b!)? running_var, Tensor(c!)? num_batches_tracked, float momentum, float eps, float raw_denominator) -> Tensor");
     m.def("mosaic_ad(Tensor raw, Tensor? black_level, bool reduce_size, int out_channels, float raw_denominator) -> Tensor");
     m.def("dihedral_copy(Tensor src, int[] map6, int h_dst, int w_dst, bool channels_last, bool to_bf16) -> Tensor");
     m.def("numpy_forward(Tensor raw, float[] black_level, float[] white_balance, float[] colour_matrix, bool sharpening_filter, "

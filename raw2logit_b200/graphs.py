@@ -10,8 +10,8 @@ read ``step.out``, ``step.grad_raw`` (fp32 input with ``need_raw_grad``) and ``s
 ``step.params`` in ``named_parameters`` order, one contiguous vector) afterwards, on the same stream.
 
 Everything the captured kernels touch lives in the graph's private memory pool; the module's parameters are read in
-place, so optimiser updates between replays are seen.  BatchNorm running statistics are updated by the replay, as in
-eager mode (``num_batches_tracked`` is the one exception: it is host-side bookkeeping and advances at capture only).
+place, so optimiser updates between replays are seen.  BatchNorm running statistics and ``num_batches_tracked`` are
+updated by the replay, as in eager mode (the forward kernel advances the counter itself).
 """
 import torch
 

@@ -55,14 +55,14 @@ def set_gradient_exchange(exchange, average=True):
 
 def fused_isp(raw, black_level, white_balance, colour_correction, gamma_correct, debayer_weight, sharpen_weight,
               gauss_weight, rgb2yuv, yuv2rgb, additive=None, bn_mode=0, running_mean=None, running_var=None,
-              momentum=0.1, eps=1e-5, raw_denominator=65535.0):
+              momentum=0.1, eps=1e-5, raw_denominator=65535.0, num_batches_tracked=None):
     """raw (B,H,W) + 7 parameter tensors + 2 buffers [+ additive] [+ BatchNorm tail] -> (B,3,H,W), differentiable in
     raw, the 7 parameter tensors and the additive layer (``FusedISPFn`` in r2l_torch.cpp).
     bn_mode: 0 = no tail, 1 = eval (affine from running statistics), 2 = train (batch statistics, running statistics
-    updated in place by the kernel)."""
+    updated in place by the kernel; ``num_batches_tracked``, when given, is incremented by the kernel as well)."""
     return _ops.fused(raw, black_level, white_balance, colour_correction, gamma_correct, debayer_weight,
                       sharpen_weight, gauss_weight, rgb2yuv, yuv2rgb, additive, int(bn_mode), running_mean,
-                      running_var, float(momentum), float(eps), float(raw_denominator))
+                      running_var, num_batches_tracked, float(momentum), float(eps), float(raw_denominator))
 
 
 def mosaic(raw, black_level=None, reduce_size=True, out_channels=3, raw_denominator=65535.0):

@@ -154,15 +154,20 @@ class ParametrizedProcessing(nn.Module):
             return self._forward_staged(raw)
 
         bn = self.batch_norm
-        bn_mode, rm, rv, momentum, eps = 0, None, None, 0.1, 1e-5
+        bn_mode, rm, rv, nbt, momentum, eps = 0, None, None, None, 0.1, 1e-5
         if bn is not None:
             eps = bn.eps
             use_batch_stats = bn.training or bn.running_mean is None
             bn_mode = 2 if use_batch_stats else 1
             rm, rv = bn.running_mean, bn.running_var
             if use_batch_stats and bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked.add_(1)                      # nn.BatchNorm2d bookkeeping
-                momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                # nn.BatchNorm2d bookkeeping: the counter is advanced by the forward kernel (no extra launch, and a
+                # captured step counts its replays); only the cumulative-average mode needs its value on the host
+                if bn.momentum is not None and bn.num_batches_tracked.is_cuda:
+                    nbt, momentum = bn.num_batches_tracked, bn.momentum
+                else:
+                    bn.num_batches_tracked.add_(1)
+                    momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
             elif use_batch_stats:
                 rm, rv = None, None                                  # batch statistics, nothing to update
         additive = self.additive_layer
@@ -173,7 +178,7 @@ class ParametrizedProcessing(nn.Module):
                             self.debayer.weight, self.sharpening_filter.weight, self.gaussian_blur.weight,
                             self.M_RGB_2_YUV, self.M_YUV_2_RGB, additive=additive, bn_mode=bn_mode,
                             running_mean=rm, running_var=rv, momentum=momentum, eps=eps,
-                            raw_denominator=float(2 ** self.raw_bits - 1))
+                            raw_denominator=float(2 ** self.raw_bits - 1), num_batches_tracked=nbt)
         self.buffer['processed_rgb'] = rgb
         return rgb
 

@@ -396,3 +396,65 @@ def test_tmem_backward_agrees_with_register_backward(shape, tail, u16):
         assert maxabs(p5, p) <= 2e-5 * max(1.0, p.abs().max().item()), (name, shape, tail, maxabs(p5, p))
         if not u16:
             assert maxabs(r5, r) <= 2e-5 * max(1.0, r.abs().max().item()), (name, shape, tail, maxabs(r5, r))
+
+
+@pytest.mark.parametrize("shape", [(6, 256, 256), (3, 72, 136)])
+def test_deferred_batchnorm_tail_equals_the_separately_finished_one(shape):
+    """Train-mode BatchNorm backward: the tail finished in the backward kernel's prologue from the statistics kernel's
+    per-CTA sums (default) against the one a separate finish kernel completes (R2L_ISP_BN_TAIL_COMPLETE=1): the same
+    sums in the same order, so every gradient is bit-identical."""
+    import os
+    from processing.pipeline_torch import ParametrizedProcessing
+    state = syn.perturbed_state(isp_oracle.default_state(syn.CAMERA_PRESETS["drone"]))
+    raw = syn.smooth_scene(*shape, "drone", seed=43).cuda()
+    g = isp_oracle.cotangent((shape[0], 3, shape[1], shape[2]), "ramp").cuda()
+    res = []
+    for mode in ("0", "1"):
+        os.environ["R2L_ISP_BN_TAIL_COMPLETE"] = mode
+        try:
+            mod = ParametrizedProcessing(syn.CAMERA_PRESETS["drone"], batch_norm_output=True)
+            mod.load_state_dict(state, strict=False)
+            mod = mod.cuda().train()
+            x = raw.clone().requires_grad_(True)
+            mod(x).backward(g)
+            res.append([x.grad.cpu().numpy()] + [p.grad.cpu().numpy() for p in mod.parameters()])
+        finally:
+            os.environ.pop("R2L_ISP_BN_TAIL_COMPLETE", None)
+    for a, b in zip(*res):
+        assert np.isfinite(a).all() and np.array_equal(a, b)
+
+
+def test_num_batches_tracked_is_advanced_by_the_forward_kernel():
+    """nn.BatchNorm2d's counter: one per train-mode forward (eager and CUDA-graph replay alike), none in eval mode; the
+    cumulative-average mode (momentum=None) keeps torch's semantics through the host path."""
+    from processing.pipeline_torch import ParametrizedProcessing
+    from raw2logit_b200.graphs import GraphedStep
+    mod = ParametrizedProcessing(syn.CAMERA_PRESETS["drone"], batch_norm_output=True).cuda().train()
+    raw = syn.smooth_scene(4, 64, 96, "drone", seed=5).cuda()
+    ref_bn = torch.nn.BatchNorm2d(3, affine=False).cuda().train()
+    plain = ParametrizedProcessing(syn.CAMERA_PRESETS["drone"], batch_norm_output=False).cuda()
+    for _ in range(3):
+        mod(raw)
+        ref_bn(plain(raw))
+    assert int(mod.batch_norm.num_batches_tracked) == 3 == int(ref_bn.num_batches_tracked)
+    assert torch.allclose(mod.batch_norm.running_mean, ref_bn.running_mean, atol=1e-6)
+    assert torch.allclose(mod.batch_norm.running_var, ref_bn.running_var, atol=1e-6)
+    mod.eval()
+    mod(raw)
+    assert int(mod.batch_norm.num_batches_tracked) == 3
+    mod.train()
+    step = GraphedStep(mod, raw, torch.full((4, 3, 64, 96), 1e-3, device="cuda"))
+    n0 = int(mod.batch_norm.num_batches_tracked)
+    step.replay()
+    step.replay()
+    torch.cuda.synchronize()
+    assert int(mod.batch_norm.num_batches_tracked) == n0 + 2
+    mod.batch_norm.momentum, ref_bn.momentum = None, None           # cumulative moving average
+    n1 = int(mod.batch_norm.num_batches_tracked)
+    ref_bn.num_batches_tracked.fill_(n1)
+    ref_bn.running_mean.copy_(mod.batch_norm.running_mean)
+    ref_bn.running_var.copy_(mod.batch_norm.running_var)
+    mod(raw)
+    ref_bn(plain(raw))
+    assert int(mod.batch_norm.num_batches_tracked) == n1 + 1
+    assert torch.allclose(mod.batch_norm.running_mean, ref_bn.running_mean, atol=1e-6)
