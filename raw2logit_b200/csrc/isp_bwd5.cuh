@@ -349,7 +349,13 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
         // gamma statistic.  o = y (or (y - shift)/scale - additive behind a tail); with lo = log2(o):
         // e = cl^(1/g - 1) = 2^((1 - g) lo), log2(cl) = g lo, and the clamp passed iff o lies strictly between its two
         // clipped values (exact compare without a tail, where o is bit-identical to the forward's; a 1e-4 / 1e-6
-        // relative margin behind a tail, where o is recovered by an affine inverse).
+        // relative margin behind a tail, where o is recovered by an affine inverse).  The margin at the low clip is
+        // 5.3e-7 absolute; the inverse's error is ~1e-7 for a BatchNorm tail (|shift / scale| <= 1: the fma is exact
+        // before its rounding, what is left are the roundings of 1/scale, shift/scale and of the stored y) and
+        // ~ulp(additive)/2 more with an additive layer -- below the margin while |additive| < 2.  Testing the stored y
+        // for equality with fma(o_clip + additive, scale, shift) instead would be exact for this library's own forward
+        // but fragile for any other producer of `out` (tried and dropped: the host emulation's tail cases feed an fp64
+        // oracle's output).
         { R2L_FOR_THREADS(NT) {
             float m2g[9];
             const float invg = T->invg, gam = T->gamma, one_m_g = 1.0f - T->gamma;
