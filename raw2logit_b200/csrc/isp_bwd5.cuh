@@ -499,11 +499,18 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     padrows |= rt[u] != 0;
                 }
                 // products of window row d (gY2 row q.y - 2 + d, columns q.x - 2 .. q.x + 5) with the tap row in w5 / acc
-                auto full = [&](int u, int d, const float (&w5)[5], f2 (&acc)[5]) {
+                // SIDE (compile time): the tile touches the left or right image border, so some item may carry pad-column
+                // work; in an interior tile column (half of them at W = 256, more on wider frames) L = R = 0 everywhere
+                // and the six per-site weights / six masked-centre products per item and tap row are not even issued
+                // (they were 20 % of this loop).  The choice is uniform over the CTA: no divergence.
+                auto full = [&](auto side_c, int u, int d, const float (&w5)[5], f2 (&acc)[5]) {
+                    constexpr bool SIDE = decltype(side_c)::value;
                     // sites 1 and 2: out[1] also receives row[3] w0 + row[2] w1 (L) and row[5] w4 (R), out[2] receives
                     // row[2] w0 (L) and row[5] w3 + row[4] w4 (R); row[i] is column q.x - 2 + i
-                    const float w1_0 = fmaf_(Rf[u], w5[4], w5[0]), w1_2 = fmaf_(Lf[u], w5[0], w5[2]), w1_3 = fmaf_(Lf[u], w5[1], w5[3]);
-                    const float w2_1 = fmaf_(Rf[u], w5[3], w5[1]), w2_2 = fmaf_(Rf[u], w5[4], w5[2]), w2_4 = fmaf_(Lf[u], w5[0], w5[4]);
+                    const float w1_0 = SIDE ? fmaf_(Rf[u], w5[4], w5[0]) : w5[0], w1_2 = SIDE ? fmaf_(Lf[u], w5[0], w5[2]) : w5[2],
+                                w1_3 = SIDE ? fmaf_(Lf[u], w5[1], w5[3]) : w5[3];
+                    const float w2_1 = SIDE ? fmaf_(Rf[u], w5[3], w5[1]) : w5[1], w2_2 = SIDE ? fmaf_(Rf[u], w5[4], w5[2]) : w5[2],
+                                w2_4 = SIDE ? fmaf_(Lf[u], w5[0], w5[4]) : w5[4];
                     f2 row[8];
                     ld8<PN>(PG, (ir[u] + 2 + d) * PN + 2 * (ig[u] + 2), row);
 #pragma unroll
@@ -518,11 +525,14 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc[bb] = fma2vv(c[u][j], row[j + 4 - bb], acc[bb]);
                     // pad sites' share of dWg: Y1pad(-1) = Y1(1), Y1pad(-2) = Y1(2), Y1pad(W) = Y1(W-2), Y1pad(W+1) = Y1(W-3)
-                    acc[0] = fma2vv(cl1[u], row[3], fma2vv(cl2[u], row[2], acc[0]));
-                    acc[1] = fma2vv(cl1[u], row[2], acc[1]);
-                    acc[3] = fma2vv(cr2[u], row[5], acc[3]);
-                    acc[4] = fma2vv(cr2[u], row[4], fma2vv(cr1[u], row[5], acc[4]));
+                    if (SIDE) {
+                        acc[0] = fma2vv(cl1[u], row[3], fma2vv(cl2[u], row[2], acc[0]));
+                        acc[1] = fma2vv(cl1[u], row[2], acc[1]);
+                        acc[3] = fma2vv(cr2[u], row[5], acc[3]);
+                        acc[4] = fma2vv(cr2[u], row[4], fma2vv(cr1[u], row[5], acc[4]));
+                    }
                 };
+                const bool side_tile = tx0 == 0 || tx0 + TW >= W;          // CTA-uniform
 #pragma unroll 1
                 for (int A = 0; A < 5; ++A) {
                     f2 acc[5];
@@ -531,7 +541,13 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
                     for (int bb = 0; bb < 5; ++bb) { acc[bb] = mk2(0.f, 0.f); w5[bb] = wg[A * 5 + bb]; }
 #pragma unroll
-                    for (int u = 0; u < NI5; ++u) full(u, 4 - A, w5, acc);
+                    if (side_tile) {
+#pragma unroll
+                        for (int u = 0; u < NI5; ++u) full(std::true_type(), u, 4 - A, w5, acc);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < NI5; ++u) full(std::false_type(), u, 4 - A, w5, acc);
+                    }
                     R2L_PARK_READY(5, wa)
 #pragma unroll
                     for (int bb = 0; bb < 5; ++bb) wa[bb] += acc[bb].x + acc[bb].y;
@@ -554,7 +570,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                             const int t = rt[u];
                             const int d = A == 0 ? (t == 2 ? 0 : (t == 1 ? 2 : -1)) : A == 1 ? (t == 1 ? 1 : -1)
                                         : A == 3 ? (t == 3 ? 3 : -1) : (t == 3 ? 2 : (t == 4 ? 4 : -1));
-                            if (d >= 0) full(u, d, w5, acc);
+                            if (d >= 0) full(std::true_type(), u, d, w5, acc);
                         }
                         R2L_PARK_READY(5, wa)
 #pragma unroll
@@ -749,7 +765,9 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                 padrows |= live[u] && (f_top[u] | f_bot[u]);
             }
             // products of window row d (g_yuv[k] row q.y - 1 + d, columns q.x - 1 .. q.x + 4) with the tap row in w / acc
-            auto full = [&](int u, const f2* pl, int d, const float (&w)[2][3], f2 (&acc)[2][3]) {
+            // SIDE as in B5: pad-column work only in the tiles of the first / last tile column
+            auto full = [&](auto side_c, int u, const f2* pl, int d, const float (&w)[2][3], f2 (&acc)[2][3]) {
+                constexpr bool SIDE = decltype(side_c)::value;
                 f2 row[6];
                 ld6<PN>(pl, (ir[u] + 3 + d) * PN + 2 * (ig[u] + 2), row);
 #pragma unroll
@@ -757,11 +775,13 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[j & 1][bb] = fma2vv(c[u][j], row[j + 2 - bb], acc[j & 1][bb]);
                 // pad sites' share of Q': rawpad(-1) = raw(1), rawpad(W) = raw(W-2)
-                acc[1][0] = fma2vv(cl1[u], row[1], acc[1][0]);
-                acc[0][2] = fma2vv(cr2[u], row[4], acc[0][2]);
+                if (SIDE) {
+                    acc[1][0] = fma2vv(cl1[u], row[1], acc[1][0]);
+                    acc[0][2] = fma2vv(cr2[u], row[4], acc[0][2]);
+                }
                 if (Cfg::GRAW) {                                        // g_raw(q) += sum_b g_yuv[k](q - (a-1, b-1)) AWq[par(q)][k][a][b]
                     // site 1 also receives row[1] w[1][0] (L), site 2 row[4] w[0][2] (R); row[i] is column q.x - 1 + i
-                    const float w1_2 = fmaf_(Lf[u], w[1][0], w[1][2]), w2_0 = fmaf_(Rf[u], w[0][2], w[0][0]);
+                    const float w1_2 = SIDE ? fmaf_(Lf[u], w[1][0], w[1][2]) : w[1][2], w2_0 = SIDE ? fmaf_(Rf[u], w[0][2], w[0][0]) : w[0][0];
 #pragma unroll
                     for (int bb = 0; bb < 3; ++bb) {
                         graw[u][0] = fma2s(row[2 - bb], w[0][bb], graw[u][0]);
@@ -771,6 +791,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     graw[u][2] = fma2s(row[4], w2_0, fma2s(row[3], w[0][1], fma2s(row[2], w[0][2], graw[u][2])));
                 }
             };
+            const bool side_tile7 = tx0 == 0 || tx0 + TW >= W;         // CTA-uniform
 #pragma unroll 1
             for (int k = 0; k < 3; ++k) {
                 const f2* pl = PU + ((k + 2) % 3) * Cfg::kF;            // k = 0: gY0 (PG), 1: gU (PU), 2: gV (PV)
@@ -786,7 +807,13 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
 #pragma unroll
                         for (int bb = 0; bb < 3; ++bb) { acc[cp][bb] = mk2(0.f, 0.f); w[cp][bb] = awq[cp * 27 + A * 3 + bb]; }
 #pragma unroll
-                    for (int u = 0; u < NI; ++u) full(u, pl, 2 - A, w, acc);
+                    if (side_tile7) {
+#pragma unroll
+                        for (int u = 0; u < NI; ++u) full(std::true_type(), u, pl, 2 - A, w, acc);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < NI; ++u) full(std::false_type(), u, pl, 2 - A, w, acc);
+                    }
                     if (A == 1) { R2L_PARK_READY(8, qa) } else { R2L_PARK_READY(6, qa) }
 #pragma unroll
                     for (int cp = 0; cp < 2; ++cp)
@@ -825,7 +852,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                             for (int bb = 0; bb < 3; ++bb) { acc[cp][bb] = mk2(0.f, 0.f); w[cp][bb] = awq[cp * 27 + A * 3 + bb]; }
 #pragma unroll
                         for (int u = 0; u < NI; ++u)
-                            if (live[u] && (A == 0 ? f_top[u] : f_bot[u])) full(u, pl, A, w, acc);
+                            if (live[u] && (A == 0 ? f_top[u] : f_bot[u])) full(std::true_type(), u, pl, A, w, acc);
                         R2L_PARK_READY(6, qa)
 #pragma unroll
                         for (int cp = 0; cp < 2; ++cp)
