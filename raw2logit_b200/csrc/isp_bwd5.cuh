@@ -540,7 +540,6 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     R2L_PARK_LOAD(5, kB5Wg + 5 * A, wa)
 #pragma unroll
                     for (int bb = 0; bb < 5; ++bb) { acc[bb] = mk2(0.f, 0.f); w5[bb] = wg[A * 5 + bb]; }
-#pragma unroll
                     if (side_tile) {
 #pragma unroll
                         for (int u = 0; u < NI5; ++u) full(std::true_type(), u, 4 - A, w5, acc);
@@ -806,7 +805,6 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                     for (int cp = 0; cp < 2; ++cp)
 #pragma unroll
                         for (int bb = 0; bb < 3; ++bb) { acc[cp][bb] = mk2(0.f, 0.f); w[cp][bb] = awq[cp * 27 + A * 3 + bb]; }
-#pragma unroll
                     if (side_tile7) {
 #pragma unroll
                         for (int u = 0; u < NI; ++u) full(std::true_type(), u, pl, 2 - A, w, acc);
@@ -827,7 +825,7 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
                             f2 row[4];
                             ld4<PN>(pl, (ir[u] + 4) * PN + 2 * (ig[u] + 2), row);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) p2[j & 1] = add2v(p2[j & 1], row[j]);
+                            for (int j = 0; j < 4; ++j) p2[j & 1] = fma2s(row[j], one, p2[j & 1]);      // one FFMA2 (two FADDs otherwise)
                         }
                         qa[6] += p2[0].x + p2[0].y; qa[7] += p2[1].x + p2[1].y;
                         R2L_PARK_STORE(2, kB5Q + kB5QStride * k + 18, qa + 6)
