@@ -1,13 +1,14 @@
 """CUDA-graph capture of the ISP training step through the module API.
 
-``GraphedStep(module, example_raw, grad_out)`` runs ``out = module(raw); out.backward(grad_out)`` a few times on a
-side stream, then captures the same two calls (C++ autograd node, forward kernel, backward kernel, gradient
-accumulation) plus the concatenation of the parameter gradients into ONE ``torch.cuda.CUDAGraph``.  A replay costs a
+``GraphedStep(module, example_raw, grad_out)`` runs ``out = module(raw); torch.autograd.grad(out, params, grad_out)`` a
+few times on a side stream, then captures the same two calls (C++ autograd node, forward kernel, backward kernel) plus
+the concatenation of the parameter gradients into ONE ``torch.cuda.CUDAGraph``.  A replay costs a
 single graph launch of host time (a few microseconds instead of ~100 us of dispatcher / autograd-engine work per step),
 which is what keeps small batches GPU-bound.  Inputs are static: write the next batch into ``step.raw`` (and, when the
 cotangent changes, ``step.grad_out``) -- e.g. with a non-blocking copy from pinned host memory -- then ``step.replay()``;
 read ``step.out``, ``step.grad_raw`` (fp32 input with ``need_raw_grad``) and ``step.flat_grads`` (the gradients of
-``step.params`` in ``named_parameters`` order, one contiguous vector) afterwards, on the same stream.
+``step.params`` in ``named_parameters`` order, one contiguous vector) afterwards, on the same stream.  The step does not
+touch ``p.grad`` of the module (``assign_grads()`` points them at the graph's tensors for an optimiser).
 
 Everything the captured kernels touch lives in the graph's private memory pool; the module's parameters are read in
 place, so optimiser updates between replays are seen.  BatchNorm running statistics and ``num_batches_tracked`` are
@@ -27,16 +28,21 @@ class GraphedStep:
                 raise TypeError("an integer raw batch has no gradient")
             self.raw.requires_grad_(True)
         self.grad_out = grad_out.detach().clone()
-        self.params = [p for p in module.parameters() if p.requires_grad]
-        kept = [p.grad for p in self.params]
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        self.params = [p for _, p in named]
+        # The captured step differentiates ALIASES of the parameters (new leaves on the same storage, so optimiser updates
+        # are seen) with torch.autograd.grad: no AccumulateGrad node takes part.  A parameter's gradient accumulator lives
+        # on the stream where an earlier eager step created it (typically the legacy default stream) for as long as any
+        # autograd graph of that step is alive; routing a captured gradient through it would make that stream wait on the
+        # capturing one, which CUDA forbids.  The module's own .grad tensors are left alone.
+        aliases = {n: p.detach().requires_grad_(True) for n, p in named}
+        inputs = list(aliases.values()) + ([self.raw] if need_raw_grad else [])
 
         def run():
-            for p in self.params:
-                p.grad = None
-            self.raw.grad = None
-            out = module(self.raw)
-            out.backward(self.grad_out)
-            return out
+            out = torch.func.functional_call(module, aliases, (self.raw,))
+            grads = torch.autograd.grad(out, inputs, self.grad_out, allow_unused=True) if inputs else ()
+            grads = [g if g is not None else torch.zeros_like(t) for g, t in zip(grads, inputs)]
+            return out, grads
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -44,18 +50,12 @@ class GraphedStep:
             for _ in range(max(1, warmup)):
                 run()
         torch.cuda.current_stream().wait_stream(side)
-        for p in self.params:
-            p.grad = None
-        self.raw.grad = None
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = run()
-            self.flat_grads = torch.cat([p.grad.reshape(-1) for p in self.params]) if self.params else None
-            self.grad_raw = self.raw.grad if need_raw_grad else None
-        # the captured gradient tensors belong to the graph; hand the module its own gradients back
-        self.param_grads = [p.grad for p in self.params]
-        for p, g in zip(self.params, kept):
-            p.grad = g
+            self.out, grads = run()
+            self.param_grads = list(grads[:len(self.params)])
+            self.flat_grads = torch.cat([g.reshape(-1) for g in self.param_grads]) if self.params else None
+            self.grad_raw = grads[len(self.params)] if need_raw_grad else None
 
     def replay(self):
         self.graph.replay()

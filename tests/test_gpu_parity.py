@@ -458,3 +458,24 @@ def test_num_batches_tracked_is_advanced_by_the_forward_kernel():
     ref_bn(plain(raw))
     assert int(mod.batch_norm.num_batches_tracked) == n1 + 1
     assert torch.allclose(mod.batch_norm.running_mean, ref_bn.running_mean, atol=1e-6)
+
+
+def test_graphed_step_after_an_eager_step_whose_graph_is_still_alive():
+    """GraphedStep must capture even when an earlier eager forward / backward on the default stream is still referenced
+    (its gradient accumulators live on that stream): the captured step differentiates parameter aliases, and its
+    gradients equal the eager ones bit for bit; the module's own .grad tensors are not touched."""
+    from processing.pipeline_torch import ParametrizedProcessing
+    from raw2logit_b200.graphs import GraphedStep
+    mod = ParametrizedProcessing(syn.CAMERA_PRESETS["drone"], batch_norm_output=False).cuda()
+    raw = syn.smooth_scene(4, 64, 96, "drone", seed=9).cuda()
+    g = isp_oracle.cotangent((4, 3, 64, 96), "ramp").cuda()
+    out = mod(raw)
+    out.backward(g, retain_graph=True)                       # `out` (and its graph) stay alive below
+    eager = torch.cat([p.grad.reshape(-1) for p in mod.parameters()]).clone()
+    kept = [p.grad for p in mod.parameters()]
+    step = GraphedStep(mod, raw, g)
+    step.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(step.flat_grads, eager)
+    assert torch.equal(step.out, out)
+    assert all(p.grad is k for p, k in zip(mod.parameters(), kept))
