@@ -20,11 +20,18 @@
 
 namespace r2l {
 
+// Row pitch of the shared-memory planes = TW + 16 sites in use + 4 pad sites.  With 80 sites (640 B) every row starts on the
+// same bank, so the halo-ring items -- a warp's lanes on one column of 16 rows -- met 16-way bank conflicts (ncu: 8.7 wavefronts
+// per 128-bit load against 3); 84 sites shift consecutive rows by 8 banks: backward 84.5 -> 83.0 us (in-call A/B; 82 sites, one
+// bank group per row, measured the same).  The pad sites are never read.
+#ifndef R2L_BWD_PN_PAD
+#define R2L_BWD_PN_PAD 20
+#endif
 template <int TH_, int TW_, int NT_, bool GRAW_, bool TAIL_> struct Bwd4Cfg {
     static constexpr int TH = TH_, TW = TW_, NT = NT_;
     static constexpr bool GRAW = GRAW_, TAIL = TAIL_;
     static constexpr int G = TW / 4;
-    static constexpr int PN = TW + 16;        // plane pitch (sites): column index = gx - x0 + 8, run q = g + 2
+    static constexpr int PN = TW + R2L_BWD_PN_PAD;   // plane pitch (sites): column index = gx - x0 + 8, run q = g + 2
     static constexpr int FH = TH + 8, G1H = TH + 4;
     static constexpr int kTableFloats = (sizeof(Tables2) + 15) / 16 * 4;
     static constexpr int kF = FH * PN, kG1 = G1H * PN;

@@ -111,10 +111,10 @@ template <int P> R2L_HD void ld4(const f2* pl, int eb, f2 v[4]) {
 // Runs (4 sites) outside the image are not stored; pad rows read the mirrored source row (reflect-1 of the mosaic,
 // pipeline_torch.py:233: -1 -> 1, H -> H-2); pad columns -1 / W are written by the first / last run of the image.
 // The outermost run on each side (beyond the halo any consumer reads) is skipped.
-template <int P, int RH, int ROFF, int COFF, int SP, int SOFF, int NT, typename RawT, bool TMA>
+template <int P, int RH, int ROFF, int COFF, int SP, int SOFF, int NT, typename RawT, bool TMA, int LW = P>
 R2L_HD void phase_deinterleave(int tid, f2* __restrict__ XR, const RawT* __restrict__ stage, const RawT* imgA,
                                const RawT* imgB, float denom, int ty0, int tx0, int H, int W, int ly0 = 0, int ly1 = RH) {
-    constexpr int Q = P / 4, QI = Q - 2;
+    constexpr int Q = LW / 4, QI = Q - 2;                               // LW: sites of a row in use (the pitch P may be padded)
 #pragma unroll 2
     for (int i = tid; i < (ly1 - ly0) * QI; i += NT) {                 // plane rows ly0 .. ly1-1
         const int lr = i / QI, lq = i - lr * QI + 1, ly = ly0 + lr;

@@ -16,9 +16,16 @@
 
 namespace r2l {
 
+// Row pitch of the haloed planes = LW sites in use + 4 pad sites, for the same reason as the backward's (isp_bwd4.cuh: rows
+// of 80 sites all start on one bank and the halo-ring items pay 16-way conflicts): forward 41.5 -> 39.6 us.  The TMA staging
+// buffer keeps the unpadded width (its box rows must be multiples of 16 bytes for 2-byte raw as well).
+#ifndef R2L_FWD_P_PAD
+#define R2L_FWD_P_PAD 20
+#endif
 template <int TH_, int TW_, int NT_> struct Fwd3Cfg {
     static constexpr int TH = TH_, TW = TW_, NT = NT_;
-    static constexpr int P = TW + 16;                 // row pitch (sites) of the haloed planes; column index = gx - x0 + 8
+    static constexpr int LW = TW + 16;                // sites of a haloed row: column index = gx - x0 + 8 (also the TMA box width)
+    static constexpr int P = TW + R2L_FWD_P_PAD;      // row pitch (sites) of the haloed planes (>= LW, a multiple of 4)
     static constexpr int RH = TH + 8, Y0H = TH + 6, Y1H = TH + 4;
     static constexpr int G = TW / 4;                  // 4-site runs per tile row
     static constexpr int kTableFloats = (sizeof(Tables2) + 15) / 16 * 4;
@@ -26,7 +33,7 @@ template <int TH_, int TW_, int NT_> struct Fwd3Cfg {
     static constexpr int kSites = kXR + kY0 + 2 * kUV;
     static constexpr size_t kPlaneBytes = (size_t)kTableFloats * 4 + (size_t)kSites * 8;
     static constexpr size_t kStageOffset = (kPlaneBytes + 127) / 128 * 128;       // TMA destination: 128-byte aligned
-    static constexpr size_t kStageBytes = (size_t)2 * RH * P * 4;                 // [image][row][P] of the raw element
+    static constexpr size_t kStageBytes = (size_t)2 * RH * LW * 4;                // [image][row][LW] of the raw element
     static constexpr size_t kSmemBytes = kPlaneBytes;
     static constexpr size_t kSmemBytesTma = kStageOffset + kStageBytes + 16;      // + staging + mbarrier
     static constexpr int HALF = NT / 2;
@@ -66,7 +73,7 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
     RawT* stage = reinterpret_cast<RawT*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + Cfg::kStageOffset + Cfg::kStageBytes);
     uint32_t tma_phase = 0;
-    constexpr uint32_t kTmaBytes = 2u * Cfg::RH * P * sizeof(RawT);
+    constexpr uint32_t kTmaBytes = 2u * Cfg::RH * Cfg::LW * sizeof(RawT);
     if (TMA && threadIdx.x == 0) {
         mbar_init(mbar, 1);
         if (cta < grid.n) {
@@ -100,7 +107,7 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
 #ifdef R2L_HOST_EMU
             const RawT* stage = nullptr;
 #endif
-            phase_deinterleave<P, Cfg::RH, 4, 8, P, 0, NT, RawT, TMA>(tid, XR, stage, imgA, imgB, a.denom, ty0, tx0, H, W);
+            phase_deinterleave<P, Cfg::RH, 4, 8, Cfg::LW, 0, NT, RawT, TMA, Cfg::LW>(tid, XR, stage, imgA, imgB, a.denom, ty0, tx0, H, W);
         } }
         R2L_SYNC();
 #ifndef R2L_HOST_EMU

@@ -48,7 +48,7 @@ template <class Cfg, typename RawT, bool STATS, bool TAIL>
 static int launch_forward3_t(const FwdArgs& a, cudaStream_t st, int* grid_used) {
     const TileGrid grid = make_grid((a.B + 1) / 2, a.H, a.W, Cfg::TH, Cfg::TW);     // tiles of image pairs
     CUtensorMap tmap;
-    if (!make_raw_tensor_map(&tmap, a.raw, (int)sizeof(RawT), a.B, a.H, a.W, Cfg::P, Cfg::RH)) return kNotServed;
+    if (!make_raw_tensor_map(&tmap, a.raw, (int)sizeof(RawT), a.B, a.H, a.W, Cfg::LW, Cfg::RH)) return kNotServed;
     int g = 0;
     int rc = persistent_grid(isp_forward3_kernel<Cfg, RawT, STATS, TAIL>, Cfg::NT, Cfg::kSmemBytesTma, grid.n, &g);
     if (rc != R2L_OK) return rc;
