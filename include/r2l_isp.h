@@ -87,7 +87,7 @@ int r2l_isp_last_cuda_error(void);
 /* Fused forward: replaces ParametrizedProcessing.forward (pipeline_torch.py:175-225) minus stage tracking:
  * raw2rgb :183 -> Debayer :187 -> WB :190 -> CCM :191 -> RGB2YUV :194 -> sharpen(Y) :195 -> Gaussian(Y) :202
  * -> YUV2RGB :203 -> clip :206 -> gamma :209 [-> additive :213] [-> eval-BN :217].  tail may be NULL. */
-/* saved_luma (NULL, or r2l_isp_saved_luma_floats(B,H,W) floats, 16-byte aligned): when given, the kernel also
+/* saved_luma (NULL, or r2l_isp_saved_luma_floats(B,H,W) floats, 32-byte aligned: written / read with 256-bit accesses): when given, the kernel also
  * keeps the two luma planes it computes on the way -- Y0 (after RGB->YUV, :194) and Y1 (after the sharpening filter,
  * :195) -- laid out [2][ceil(B/2)][H][W][2] (images 2p, 2p+1 interleaved per site; an odd last image is paired with
  * itself).  They are what torch autograd would keep for the two convolutions' weight gradients; handing them to

@@ -46,8 +46,17 @@ inline bool bwd4_shape_ok(int H, int W) { return (W % 4) == 0 && H >= 8 && W >= 
 
 // 4 sites x (image A, image B) of a saved luma plane: 32 contiguous bytes, read once
 R2L_HD void ld_luma4(const float* p, f2 c[4]) {
+#ifdef R2L_HOST_EMU
     const f4 v0 = ld_stream4(p), v1 = ld_stream4(p + 4);
     c[0] = mk2(v0.x, v0.y); c[1] = mk2(v0.z, v0.w); c[2] = mk2(v1.x, v1.y); c[3] = mk2(v1.z, v1.w);
+#else
+    // ONE 256-bit load (sm_100: LDG.E.256, L2 only like ld_stream4): as two 128-bit loads every warp instruction touched
+    // only half of each 32-byte sector it requested (the lane stride is 32 bytes).  p is 32-byte aligned.
+    float v[8];
+    asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+    c[0] = mk2(v[0], v[1]); c[1] = mk2(v[2], v[3]); c[2] = mk2(v[4], v[5]); c[3] = mk2(v[6], v[7]);
+#endif
 }
 
 #ifndef R2L_HOST_EMU

@@ -37,7 +37,7 @@ template <typename RawT>
 static int launch_backward5_impl(const BwdArgs& a, cudaStream_t st, int* grid_used) {
     if (!a.out || !a.luma || !bwd5_shape_ok(a.H, a.W)) return kNotServed;
     if (!aligned(a.gout, 16) || !aligned(a.graw, 16) || !aligned(a.additive, 16) || !aligned(a.out, 16) ||
-        !aligned(a.luma, 16) || !aligned(a.raw, 4 * sizeof(RawT)))
+        !aligned(a.luma, 32) || !aligned(a.raw, 4 * sizeof(RawT)))
         return kNotServed;                                                          // 128-bit rows
     const bool tail = a.gtail != nullptr;
     constexpr int CPS = kBwd5CtasPerSm;

@@ -22,6 +22,18 @@ namespace r2l {
 #ifndef R2L_FWD_P_PAD
 #define R2L_FWD_P_PAD 20
 #endif
+// 4 sites x (image A, image B) of a saved luma plane: 32 contiguous, 32-byte aligned bytes written by ONE 256-bit store
+// (sm_100: STG.E.256) -- as two 128-bit stores each warp instruction filled only half of every sector it touched
+R2L_HD void st_luma4(float* dst, f2 a0, f2 a1, f2 a2, f2 a3) {
+#ifdef R2L_HOST_EMU
+    st2(reinterpret_cast<f2*>(dst), a0, a1);
+    st2(reinterpret_cast<f2*>(dst) + 2, a2, a3);
+#else
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(dst), "f"(a0.x), "f"(a0.y), "f"(a1.x), "f"(a1.y), "f"(a2.x), "f"(a2.y), "f"(a3.x), "f"(a3.y) : "memory");
+#endif
+}
+
 template <int TH_, int TW_, int NT_> struct Fwd3Cfg {
     static constexpr int TH = TH_, TW = TW_, NT = NT_;
     static constexpr int LW = TW + 16;                // sites of a haloed row: column index = gx - x0 + 8 (also the TMA box width)
@@ -172,8 +184,7 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
                 }
                 else if (a.luma) {                     // owned, in the image: keep Y0 for the backward's dWs statistic
                     float* dst = a.luma + (((size_t)(b0 >> 1) * H + (ty0 + r)) * W + (tx0 + 4 * g)) * 2;
-                    st2(reinterpret_cast<f2*>(dst), acc[0][0], acc[1][0]);
-                    st2(reinterpret_cast<f2*>(dst) + 2, acc[2][0], acc[3][0]);
+                    st_luma4(dst, acc[0][0], acc[1][0], acc[2][0], acc[3][0]);
                 }
                 st4<P>(Y0, (r + 3) * P + 2 * q, acc[0][0], acc[1][0], acc[2][0], acc[3][0]);
                 st4<TW>(U, r * TW + 2 * g, acc[0][1], acc[1][1], acc[2][1], acc[3][1]);
@@ -288,8 +299,7 @@ R2L_HD void fwd3_cta(int cta, int n_cta, const FwdArgs& a, const TileGrid& grid,
                     const int rr = rr0 + o, gy = gy0 + o;
                     if (a.luma && rr >= 2 && rr < TH + 2 && g >= 0 && g < G && gy < H) {     // owned, in the image: keep Y1
                         float* dst = a.luma + ((((size_t)((a.B + 1) >> 1) + (b0 >> 1)) * H + gy) * W + gx) * 2;
-                        st2(reinterpret_cast<f2*>(dst), acc[o][0], acc[o][1]);
-                        st2(reinterpret_cast<f2*>(dst) + 2, acc[o][2], acc[o][3]);
+                        st_luma4(dst, acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
                     }
                     st4<P>(Y1, rr * P + 2 * q, acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
                     if (gx == 0) { Y1[rr * P + phys<P>(4 * q - 1)] = acc[o][1]; Y1[rr * P + phys<P>(4 * q - 2)] = acc[o][2]; }

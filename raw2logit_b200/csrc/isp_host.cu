@@ -603,7 +603,7 @@ int r2l_isp_forward(const void* raw, int raw_dtype, float raw_denominator, int B
     if (B == 0) return R2L_OK;
     if (!out) return R2L_ERR_NULL_POINTER;
     if (!aligned(out, 4)) return R2L_ERR_MISALIGNED;
-    if (saved_luma && (!aligned(saved_luma, 16) || !luma_path_ok(raw, raw_dtype, H, W, out, tail ? tail->additive : nullptr)))
+    if (saved_luma && (!aligned(saved_luma, 32) || !luma_path_ok(raw, raw_dtype, H, W, out, tail ? tail->additive : nullptr)))
         return R2L_ERR_BAD_ARGUMENT;                           // ask r2l_isp_luma_supported first
     FwdArgs a;
     a.luma = saved_luma;
@@ -638,7 +638,7 @@ int r2l_isp_forward_bn_train(const void* raw, int raw_dtype, float raw_denominat
     int rc = check_common(raw, raw_dtype, B, H, W, params);
     if (rc != R2L_OK) return rc;
     if (!out || !saved_affine || !workspace) return R2L_ERR_NULL_POINTER;
-    if (saved_luma && (!aligned(saved_luma, 16) || !luma_path_ok(raw, raw_dtype, H, W, out, additive)))
+    if (saved_luma && (!aligned(saved_luma, 32) || !luma_path_ok(raw, raw_dtype, H, W, out, additive)))
         return R2L_ERR_BAD_ARGUMENT;
     if (!aligned(out, 4) || !aligned(workspace, 8)) return R2L_ERR_MISALIGNED;
     if (workspace_bytes < r2l_isp_workspace_bytes(B, H, W)) return R2L_ERR_WORKSPACE;
