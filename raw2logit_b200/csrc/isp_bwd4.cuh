@@ -70,6 +70,10 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // per warp (40 independent 4-byte loads per lane) so the whole read is a handful of L2 round trips.
 // scratch: doubles, [NW][kStatPitch] + kNumStats + 108 + 9 + 4 + 9
 template <int NT>
+__device__ __forceinline__ void finish_chain_rule(const Tables* T, const double* S, float* grads, double* Qr, double* Tkc,
+                                                  double* Gbl, double* Sc9);
+
+template <int NT>
 __device__ __forceinline__ void fused_finish(const Tables* T, const float* partials, int n_cta, float* grads, double* scratch) {
     constexpr int NW = NT / 32, SPL = kStatPitch / 32;              // 5 statistics per lane
     static_assert(kStatPitch % 32 == 0, "one CTA row = SPL coalesced warp loads");
@@ -109,6 +113,15 @@ __device__ __forceinline__ void fused_finish(const Tables* T, const float* parti
         S[s] = t;
     }
     __syncthreads();
+    finish_chain_rule<NT>(T, S, grads, Qr, Tkc, Gbl, Sc9);
+}
+
+// stages 3 - 5 of the finish: the 155 sums S (shared memory, complete and visible to the CTA) -> the 132 gradients
+template <int NT>
+__device__ __forceinline__ void finish_chain_rule(const Tables* T, const double* S, float* grads, double* Qr, double* Tkc,
+                                                  double* Gbl, double* Sc9) {
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 108; i += NT) { const int k = i / 36, r = i - 36 * k; Qr[i] = finish_qr(S, T, k, r / 9, r % 9); }
     __syncthreads();
     for (int job = warp; job < 13; job += NW) {
@@ -143,6 +156,73 @@ __device__ __forceinline__ void fused_finish(const Tables* T, const float* parti
     }
     __syncthreads();
     for (int e = tid; e < R2L_NUM_PARAM_GRADS; e += NT) grads[e] = e < 4 ? (float)Gbl[e] : finish_grad_sc(e, S, T, Sc9);
+}
+
+// ---- two-level finish (fifth generation) --------------------------------------------------------------------------
+// The one-level finish above is a serial tail: the last CTA reads all n_cta rows while the rest of the GPU is idle
+// (7.3 us of an 82 us launch, profiles/r02_experiments.md).  Here the CTAs form kFinishGroups static groups of consecutive
+// CTA indices; the last CTA of a GROUP to arrive sums that group's rows (a few rows per warp: one L2 round trip) into one
+// fp64 row, and only the last group finisher adds the <= 16 group rows and runs the chain rule.  No CTA ever waits for
+// another one.  The order of every addition is fixed by CTA index, so the result is reproducible run to run.
+constexpr int kFinishGroups = 16;
+// the group rows live behind the per-CTA rows of the workspace: the last 32 of its kMaxCtas rows = 16 x 160 doubles
+constexpr int kFinishMaxCtas = kMaxCtas - kFinishGroups * 2;
+__device__ __forceinline__ double* finish_group_rows(float* partials) {
+    return reinterpret_cast<double*>(partials + (size_t)kFinishMaxCtas * kStatPitch);
+}
+__device__ __forceinline__ int finish_group_size(int n_cta) { return (n_cta + kFinishGroups - 1) / kFinishGroups; }
+
+// rows c0 .. c1-1 of the per-CTA partials -> out[kStatPitch] (global, fp64).  scratch: [NW][kStatPitch] doubles.
+template <int NT>
+__device__ __forceinline__ void finish_group_sum(const float* partials, int c0, int c1, double* out, double* scratch) {
+    constexpr int NW = NT / 32, SPL = kStatPitch / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double sum[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) sum[i] = 0.0;
+    for (int c = c0 + warp; c < c1; c += 3 * NW) {                   // warp w: rows c0 + w, + NW, + 2 NW, ... (three in flight)
+        float v[3][SPL];
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+#pragma unroll
+            for (int i = 0; i < SPL; ++i)
+                v[u][i] = (c + u * NW < c1) ? __ldcg(partials + (size_t)(c + u * NW) * kStatPitch + i * 32 + lane) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) sum[i] += (double)v[u][i];
+    }
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) scratch[warp * kStatPitch + i * 32 + lane] = sum[i];
+    __syncthreads();
+    for (int s = tid; s < kStatPitch; s += NT) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t += scratch[w * kStatPitch + s];
+        out[s] = t;
+    }
+}
+
+// the ng group rows -> S (shared) -> the 132 gradients.  scratch: kStatPitch + 108 + 9 + 4 + 9 doubles.
+template <int NT>
+__device__ __forceinline__ void finish_from_groups(const Tables* T, const double* rows, int ng, float* grads, double* scratch) {
+    double* S = scratch;
+    double* Qr = S + kStatPitch;
+    double* Tkc = Qr + 108;
+    double* Gbl = Tkc + 9;
+    double* Sc9 = Gbl + 4;
+    const int tid = threadIdx.x;
+    for (int s = tid; s < kStatPitch; s += NT) {
+        double v[kFinishGroups];
+#pragma unroll
+        for (int g = 0; g < kFinishGroups; ++g) v[g] = g < ng ? __ldcg(rows + (size_t)g * kStatPitch + s) : 0.0;
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < kFinishGroups; ++g) t += v[g];
+        S[s] = t;
+    }
+    __syncthreads();
+    finish_chain_rule<NT>(T, S, grads, Qr, Tkc, Gbl, Sc9);
 }
 #endif
 

@@ -936,17 +936,35 @@ R2L_HD void bwd5_cta(int cta, int n_cta, const BwdArgs& a, const TileGrid& grid,
     } }
 #ifndef R2L_HOST_EMU
     if (a.ticket) {
+        // Two-level finish (isp_bwd4.cuh): the last CTA of each static group sums the group's rows, the last group
+        // finisher adds the group rows and runs the chain rule.  Tickets: word 0 = the groups, words 16 .. 31 = one per group
+        // (the launch-tagged 64-bit words of take_ticket; bytes 128 .. 255 of the workspace's ticket block).
         __shared__ unsigned last_flag;
+        const int gs = finish_group_size(n_cta), grp = cta / gs;
+        const int c0 = grp * gs, c1 = min(n_cta, c0 + gs), ng = (n_cta + gs - 1) / gs;
+        unsigned* gticket = a.ticket + 2 * (kFinishGroups + grp);
+        double* rows = finish_group_rows(a.partials);
+        double* scratch = reinterpret_cast<double*>(PU);
+        static_assert((size_t)(NT / 32) * kStatPitch * 8 <= (size_t)Cfg::kSites * 8 &&
+                      (size_t)(kStatPitch + 130) * 8 <= (size_t)Cfg::kSites * 8, "finish scratch fits the planes");
         __threadfence();                                             // this CTA's partial sums are visible device-wide ...
         __syncthreads();
-        if (threadIdx.x == 0) last_flag = take_ticket(a.ticket, a.ticket_gen) == (unsigned)n_cta - 1u;   // ... before its ticket is
+        if (threadIdx.x == 0) last_flag = take_ticket(gticket, a.ticket_gen) == (unsigned)(c1 - c0) - 1u;   // ... before its ticket is
         __syncthreads();
-        if (last_flag) {
+        if (last_flag) {                                             // last of its group: the group's rows -> one fp64 row
             __threadfence();
-            static_assert((size_t)(NT / 32 + 1) * kStatPitch * 8 + 130 * 8 <= (size_t)Cfg::kSites * 8, "finish scratch fits the planes");
-            if (threadIdx.x == 0) clear_ticket(a.ticket);
-            fused_finish<NT>(T, a.partials, n_cta, a.grads, reinterpret_cast<double*>(PU));
-            if (a.world > 1) peer_allreduce<NT>(a);
+            if (threadIdx.x == 0) clear_ticket(gticket);
+            finish_group_sum<NT>(a.partials, c0, c1, rows + (size_t)grp * kStatPitch, scratch);
+            __threadfence();                                         // the group row is visible before the group's ticket
+            __syncthreads();
+            if (threadIdx.x == 0) last_flag = take_ticket(a.ticket, a.ticket_gen) == (unsigned)ng - 1u;
+            __syncthreads();
+            if (last_flag) {                                         // last group: group rows -> gradients
+                __threadfence();
+                if (threadIdx.x == 0) clear_ticket(a.ticket);
+                finish_from_groups<NT>(T, rows, ng, a.grads, scratch);
+                if (a.world > 1) peer_allreduce<NT>(a);
+            }
         }
     }
 #endif

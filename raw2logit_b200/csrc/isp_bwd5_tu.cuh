@@ -18,7 +18,7 @@ static int launch_backward5_t(const BwdArgs& a, cudaStream_t st, int* grid_used)
                                   Cfg::kTmemCols, CPS, &g);
     if (rc != R2L_OK) return rc;
     if (g > grid.n) g = grid.n;
-    if (g > kMaxCtas) g = kMaxCtas;
+    if (g > kFinishMaxCtas) g = kFinishMaxCtas;                 // the last rows of the workspace hold the finish's group rows
     if (rc != R2L_OK) return rc;
     Bwd5Maps maps;
     // default 0x33: both groups of boxes at the start of B7 (in-call A/B, profiles/r02_experiments.md: 89.3 us without,

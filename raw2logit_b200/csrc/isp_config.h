@@ -26,5 +26,4 @@ constexpr int kBwd4CtasPerSm = 2;
 #endif
 template <bool GRAW, bool TAIL> using Bwd5 = Bwd5Cfg<R2L_B5_TH, 64, R2L_B5_NT, GRAW, TAIL>;
 constexpr int kBwd5CtasPerSm = R2L_B5_CPS;
-constexpr int kMaxCtas = 2048;          // upper bound on persistent CTAs == rows of the statistics workspace
 }  // namespace r2l

@@ -443,6 +443,7 @@ struct BwdAcc {
 };
 constexpr int kStatGamma = 0, kStatWg = 1, kStatWs = 26, kStatQ = 35, kStatP = 143, kNumStats = 155;
 constexpr int kStatPitch = 160;
+constexpr int kMaxCtas = 2048;          // upper bound on persistent CTAs == rows of the statistics workspace
 // exchange buffer of the fused all-reduce: [2 epoch parities][world][kSlotPitch] 8-byte words {value, epoch tag}
 constexpr int kSlotPitch = 136, kMaxWorld = 16;
 R2L_HD int stat_q_index(int k, int par, int t) { return kStatQ + (k * 4 + par) * 9 + t; }
