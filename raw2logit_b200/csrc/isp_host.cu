@@ -489,7 +489,9 @@ bool make_bwd5_prefetch_maps(Bwd5Maps* m, const BwdArgs& a, int raw_elem_bytes, 
     return true;
 }
 
-// the fused finish's ticket counter lives behind the per-CTA statistics rows of the workspace
+// the ticket words live behind the per-CTA statistics rows of the workspace: bytes 0..7 the backward's final ticket,
+// 64..79 the fused BatchNorm forward's barrier words, 128..255 the 16 group tickets of the backward's two-level finish
+// (isp_bwd4.cuh), whose 16 fp64 group rows occupy the last 32 statistics rows (kFinishMaxCtas caps that kernel's grid)
 constexpr size_t kTicketOffset = (size_t)kMaxCtas * kStatPitch * sizeof(float);
 // behind the 256 bytes of ticket words: the BatchNorm backward's per-CTA sums (deferred tail) and a resolved tail
 constexpr size_t kBnPartialsOffset = kTicketOffset + 256;
