@@ -64,7 +64,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #endif
 
 #ifndef R2L_HOST_EMU
-// ---- fused finish: the last CTA to publish its partial sums turns them into the 132 gradients ------------------
+// ---- fused finish, one level (fourth generation; the fifth uses the two-level finish further down, which shares the chain
+// rule): the last CTA to publish its partial sums turns them into the 132 gradients ------------------
 // Same arithmetic and summation order as isp_backward_finish_kernel (isp_host.cu): per-CTA partials are summed in
 // double in CTA order (bit-reproducible), then the chain rule of finish_grad_sc.  Loads are issued 8 CTA rows deep
 // per warp (40 independent 4-byte loads per lane) so the whole read is a handful of L2 round trips.
