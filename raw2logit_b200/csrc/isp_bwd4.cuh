@@ -168,6 +168,9 @@ __device__ __forceinline__ void finish_chain_rule(const Tables* T, const double*
 constexpr int kFinishGroups = 16;
 // the group rows live behind the per-CTA rows of the workspace: the last 32 of its kMaxCtas rows = 16 x 160 doubles
 constexpr int kFinishMaxCtas = kMaxCtas - kFinishGroups * 2;
+static_assert((size_t)kFinishGroups * kStatPitch * sizeof(double) <= (size_t)(kMaxCtas - kFinishMaxCtas) * kStatPitch * sizeof(float),
+              "the group rows fit the workspace rows the capped grid never uses");
+static_assert(128 + kFinishGroups * 8 <= 256, "the group tickets fit the workspace's 256-byte ticket block (isp_host.cu)");
 __device__ __forceinline__ double* finish_group_rows(float* partials) {
     return reinterpret_cast<double*>(partials + (size_t)kFinishMaxCtas * kStatPitch);
 }
