@@ -35,6 +35,12 @@ def test_argument_validation_happens_before_any_cuda_call(lib):
     assert lib.r2l_isp_forward(None, 7, 65535.0, 1, 8, 8, ctypes.byref(p), None, None, None, None) == -2   # dtype
     assert lib.r2l_isp_forward(None, 0, 65535.0, 1, 2, 8, ctypes.byref(p), None, None, None, None) == -1   # H < 3
     assert lib.r2l_isp_forward(None, 0, 65535.0, 1, 8, 8, ctypes.byref(p), None, None, None, None) == -3   # null raw
+    # saved_luma is written with 256-bit stores: a pointer that is only 16-byte aligned is refused (include/r2l_isp.h)
+    vp = ctypes.c_void_p
+    raw, out = vp(0x10000), vp(0x20000)
+    assert lib.r2l_isp_forward(raw, 0, 65535.0, 2, 64, 64, ctypes.byref(p), None, out, vp(0x30010), None) == -7
+    assert lib.r2l_isp_luma_supported(raw, 0, 2, 64, 64, out, None) == 1
+    assert lib.r2l_isp_luma_supported(raw, 0, 2, 64, 62, out, None) == 0                             # W % 4 != 0
     assert lib.r2l_isp_mosaic(None, 0, 1.0, 1, 7, 8, None, 1, 3, None, None) == -1                   # odd + packed
     assert lib.r2l_isp_mosaic(None, 0, 1.0, 1, 8, 8, None, 1, 5, None, None) == -7                   # channels
 
